@@ -1,0 +1,294 @@
+"""Python host API over the C ABI (include/cngp.h).
+
+`GpContext` is one GPU context.  Every method takes either host arrays (numpy / CPU torch tensors, pinned or not:
+the library copies in and out inside the call) or CUDA torch tensors (device pointers are passed straight through
+and the kernels are enqueued on torch's current stream).  Nothing here computes: it only marshals pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Union
+
+import numpy as np
+
+from . import _lib as L
+
+try:  # torch is plumbing (device memory, streams, torch.distributed); the library itself does not need it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+class CngpError(RuntimeError):
+    pass
+
+
+def parse_kernel(text: Union[str, L.Kernel]) -> L.Kernel:
+    """'rbf*brownian', 'se+periodic', '(rbf+linear)*brownian+white' ... -> postfix program (cngp_kernel)."""
+    if isinstance(text, L.Kernel):
+        return text
+    k = L.Kernel()
+    rc = L.load().cngp_kernel_parse(text.encode(), C.byref(k))
+    if rc != 0:
+        raise CngpError(f"cannot parse kernel expression {text!r} (rc={rc})")
+    return k
+
+
+def _is_cuda(a) -> bool:
+    return torch is not None and isinstance(a, torch.Tensor) and a.is_cuda
+
+
+class _Arg:
+    """Pointer + keep-alive for one array argument."""
+
+    def __init__(self, a, dtype, device_mode: bool, allow_none=False):
+        self.keep = None
+        self.ptr = None
+        if a is None:
+            assert allow_none
+            return
+        if device_mode:
+            tdt = torch.float64 if dtype == np.float64 else torch.int32
+            if not _is_cuda(a):
+                raise CngpError("mixing host and device arrays in one call")
+            if a.dtype != tdt or not a.is_contiguous():
+                a = a.to(tdt).contiguous()
+            self.keep = a
+            self.ptr = a.data_ptr()
+        else:
+            if torch is not None and isinstance(a, torch.Tensor):
+                tdt = torch.float64 if dtype == np.float64 else torch.int32
+                if a.dtype != tdt or not a.is_contiguous():
+                    a = a.to(tdt).contiguous()
+                self.keep = a
+                self.ptr = a.data_ptr()
+            else:
+                a = np.ascontiguousarray(a, dtype=dtype)
+                self.keep = a
+                self.ptr = a.ctypes.data
+
+
+class GpContext:
+    def __init__(self, device: int = 0, jitter_retry: bool = False, scratch_bytes: int = 0):
+        self.lib = L.load()
+        cfg = L.Config()
+        self.lib.cngp_default_config(C.byref(cfg))
+        cfg.device = device
+        cfg.jitter_retry = int(jitter_retry)
+        cfg.scratch_bytes = scratch_bytes
+        h = C.c_void_p()
+        rc = self.lib.cngp_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise CngpError(f"cngp_create failed (rc={rc}): {self.lib.cngp_last_error(None).decode()}")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cngp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise CngpError(f"{what} failed (rc={rc}): {self.lib.cngp_last_error(self.h).decode()}")
+
+    def sync(self):
+        self._check(self.lib.cngp_sync(self.h), "cngp_sync")
+
+    def launch_count(self) -> int:
+        return int(self.lib.cngp_launch_count(self.h))
+
+    def _bind_stream(self, device_mode: bool):
+        if device_mode:
+            self.lib.cngp_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        else:
+            self.lib.cngp_set_stream(self.h, None)
+
+    def _empty(self, shape, dtype, device_mode, like=None):
+        if device_mode:
+            return torch.empty(shape, dtype=torch.float64 if dtype == np.float64 else torch.int32,
+                               device=f"cuda:{self.device}")
+        return np.empty(shape, dtype=dtype)
+
+    # ------------------------------------------------------------------------------------------------------
+    def predict(self, kernel, theta, x, y, xstar, want_lml: bool = True, out=None):
+        """Exact-GP predictive mean / variance for B windows.  theta [P] or [B,P]; x, y [B,N]; xstar [M] or [B,M].
+
+        Returns (mean [B,M], var [B,M], lml [B] or None, status [B]).  `out` = (mean, var, lml, status) buffers to
+        reuse (host: numpy or pinned torch tensors; device: CUDA tensors)."""
+        k = parse_kernel(kernel)
+        dev = _is_cuda(x)
+        B, N = x.shape
+        P = k.n_params + 1
+        th_shape = tuple(theta.shape)
+        theta_stride = 0 if len(th_shape) == 1 else th_shape[1]
+        if th_shape[-1] != P:
+            raise CngpError(f"theta has {th_shape[-1]} entries, kernel needs {P} (noise last)")
+        xs_shape = tuple(xstar.shape)
+        M = xs_shape[-1]
+        xstar_stride = 0 if len(xs_shape) == 1 else M
+        if out is None:
+            mean = self._empty((B, M), np.float64, dev)
+            var = self._empty((B, M), np.float64, dev)
+            lml = self._empty((B,), np.float64, dev) if want_lml else None
+            status = self._empty((B,), np.int32, dev)
+        else:
+            mean, var, lml, status = out
+        a = [_Arg(theta, np.float64, dev), _Arg(x, np.float64, dev), _Arg(y, np.float64, dev),
+             _Arg(xstar, np.float64, dev), _Arg(mean, np.float64, dev), _Arg(var, np.float64, dev),
+             _Arg(lml, np.float64, dev, True), _Arg(status, np.int32, dev)]
+        self._bind_stream(dev)
+        rc = self.lib.cngp_predict_batch(self.h, C.byref(k), a[0].ptr, theta_stride, a[1].ptr, a[2].ptr, a[3].ptr,
+                                         xstar_stride, B, N, M, a[4].ptr, a[5].ptr, a[6].ptr, a[7].ptr,
+                                         L.MEM_DEVICE if dev else L.MEM_HOST)
+        self._check(rc, "cngp_predict_batch")
+        return mean, var, lml, status
+
+    def lml_grad(self, kernel, theta, x, y, want_grad: bool = True):
+        """LML (and d LML / d theta) for C candidates x B windows.  theta [C,P]; returns lml [C,B], grad [C,B,P], status."""
+        k = parse_kernel(kernel)
+        dev = _is_cuda(x)
+        B, N = x.shape
+        Cn, P = theta.shape
+        if P != k.n_params + 1:
+            raise CngpError(f"theta has {P} entries, kernel needs {k.n_params + 1} (noise last)")
+        lml = self._empty((Cn, B), np.float64, dev)
+        grad = self._empty((Cn, B, P), np.float64, dev) if want_grad else None
+        status = self._empty((Cn, B), np.int32, dev)
+        a = [_Arg(theta, np.float64, dev), _Arg(x, np.float64, dev), _Arg(y, np.float64, dev),
+             _Arg(lml, np.float64, dev), _Arg(grad, np.float64, dev, True), _Arg(status, np.int32, dev)]
+        self._bind_stream(dev)
+        rc = self.lib.cngp_lml_grad_batch(self.h, C.byref(k), a[0].ptr, Cn, a[1].ptr, a[2].ptr, B, N, a[3].ptr,
+                                          a[4].ptr, a[5].ptr, L.MEM_DEVICE if dev else L.MEM_HOST)
+        self._check(rc, "cngp_lml_grad_batch")
+        return lml, grad, status
+
+    def optimize(self, kernel, x, y, theta0=None, max_iters: int = 1000):
+        """Batched m.optimize(): returns (theta [B,P], lml [B], iters [B]).  Host arrays only."""
+        k = parse_kernel(kernel)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        B, N = x.shape
+        P = k.n_params + 1
+        if theta0 is None:
+            theta0 = np.ones(P)
+        theta0 = np.ascontiguousarray(theta0, dtype=np.float64)
+        stride = 0 if theta0.ndim == 1 else P
+        theta = np.empty((B, P))
+        lml = np.empty(B)
+        iters = np.empty(B, dtype=np.int32)
+        self._bind_stream(False)
+        rc = self.lib.cngp_optimize_batch(self.h, C.byref(k), theta0.ctypes.data, stride, x.ctypes.data, y.ctypes.data,
+                                          B, N, max_iters, theta.ctypes.data, lml.ctypes.data, iters.ctypes.data)
+        self._check(rc, "cngp_optimize_batch")
+        return theta, lml, iters
+
+    def gp_slip(self, kernel, time_array, slip_array, theta=None, horizon: int = 600):
+        """The node callback for B windows [B,n]: returns (mean [B,m], sigma [B,m], status [B]); sigma = 2 sqrt(var)."""
+        k = parse_kernel(kernel)
+        t = np.ascontiguousarray(time_array, dtype=np.float64)
+        s = np.ascontiguousarray(slip_array, dtype=np.float64)
+        B, n = t.shape
+        span = float(t.max() - t.min())
+        m_cap = int(np.ceil(span)) + horizon + 2
+        mean = np.empty((B, m_cap))
+        sigma = np.empty((B, m_cap))
+        m_out = C.c_int32(0)
+        status = np.empty(B, dtype=np.int32)
+        if theta is not None:
+            theta = np.ascontiguousarray(theta, dtype=np.float64)
+            stride = 0 if theta.ndim == 1 else theta.shape[1]
+            tptr = theta.ctypes.data
+        else:
+            stride, tptr = 0, None
+        self._bind_stream(False)
+        rc = self.lib.cngp_gp_slip_batch(self.h, C.byref(k), tptr, stride, t.ctypes.data, s.ctypes.data, B, n, horizon,
+                                         m_cap, mean.ctypes.data, sigma.ctypes.data, C.addressof(m_out),
+                                         status.ctypes.data)
+        self._check(rc, "cngp_gp_slip_batch")
+        m = m_out.value
+        return mean[:, :m].copy(), sigma[:, :m].copy(), status
+
+    # ------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def stop_config(**over) -> L.StopConfig:
+        c = L.StopConfig()
+        L.load().cngp_default_stop_config(C.byref(c))
+        for key, v in over.items():
+            if key in ("init_llh", "init_ecef"):
+                for j in range(3):
+                    getattr(c, key)[j] = float(v[j])
+            else:
+                setattr(c, key, v)
+        return c
+
+    def zupt_lookahead(self, mean, sigma, P, Q, STM, Hvec, pos, cfg: Optional[L.StopConfig] = None):
+        """Batched GpPredictor look-ahead.  mean, sigma [B,M]; each of P,Q,STM ([225] or [B,225]), Hvec ([60] or
+        [B,60]), pos ([3] or [B,3]) is shared or per window.  Returns dict(triggered, i_stop, step_stop, xy_err)."""
+        dev = _is_cuda(mean)
+        B, M = mean.shape
+        cfg = cfg or self.stop_config()
+        mask = 0
+        ctx_args = []
+        for bit, (arr, sz) in enumerate(zip((P, Q, STM, Hvec, pos), (225, 225, 225, 60, 3))):
+            shape = tuple(arr.shape)
+            n_el = int(np.prod(shape))
+            if len(shape) >= 2 and shape[0] == B and n_el == sz * B:
+                mask |= 1 << bit          # one entry per window
+            elif n_el != sz:
+                raise CngpError(f"context array {bit} has {n_el} elements, expected {sz} or [{B},{sz}]")
+            ctx_args.append(_Arg(arr, np.float64, dev))
+        trig = self._empty((B,), np.int32, dev)
+        i_stop = self._empty((B,), np.int32, dev)
+        step = self._empty((B,), np.int32, dev)
+        xy = self._empty((B,), np.float64, dev)
+        a = [_Arg(mean, np.float64, dev), _Arg(sigma, np.float64, dev), _Arg(trig, np.int32, dev),
+             _Arg(i_stop, np.int32, dev), _Arg(step, np.int32, dev), _Arg(xy, np.float64, dev)]
+        self._bind_stream(dev)
+        rc = self.lib.cngp_zupt_lookahead_batch(self.h, a[0].ptr, a[1].ptr, B, M, *[c.ptr for c in ctx_args], mask,
+                                                C.byref(cfg), a[2].ptr, a[3].ptr, a[4].ptr, a[5].ptr,
+                                                L.MEM_DEVICE if dev else L.MEM_HOST)
+        self._check(rc, "cngp_zupt_lookahead_batch")
+        return dict(triggered=trig, i_stop=i_stop, step_stop=step, xy_err=xy)
+
+    def llh_to_enu(self, llh, cfg: Optional[L.StopConfig] = None):
+        dev = _is_cuda(llh)
+        n = int(np.prod(tuple(llh.shape))) // 3
+        cfg = cfg or self.stop_config()
+        enu = self._empty((n, 3), np.float64, dev)
+        a = [_Arg(llh, np.float64, dev), _Arg(enu, np.float64, dev)]
+        self._bind_stream(dev)
+        rc = self.lib.cngp_llh_to_enu(self.h, a[0].ptr, n, C.byref(cfg), a[1].ptr, L.MEM_DEVICE if dev else L.MEM_HOST)
+        self._check(rc, "cngp_llh_to_enu")
+        return enu
+
+    def chol_large(self, kernel, theta, x, y, want_alpha: bool = False):
+        """Single large window (N up to 32768+): returns dict(logdet, quad, lml[, alpha])."""
+        k = parse_kernel(kernel)
+        dev = _is_cuda(x)
+        N = int(np.prod(tuple(x.shape)))
+        outs = self._empty((3,), np.float64, False)
+        alpha = self._empty((N,), np.float64, dev) if want_alpha else None
+        a = [_Arg(theta, np.float64, dev), _Arg(x, np.float64, dev), _Arg(y, np.float64, dev),
+             _Arg(alpha, np.float64, dev, True)]
+        self._bind_stream(dev)
+        if dev:
+            o = torch.empty(3, dtype=torch.float64, device=f"cuda:{self.device}")
+            rc = self.lib.cngp_chol_large(self.h, C.byref(k), a[0].ptr, a[1].ptr, a[2].ptr, N, o.data_ptr(),
+                                          o.data_ptr() + 8, o.data_ptr() + 16, a[3].ptr, L.MEM_DEVICE)
+            self._check(rc, "cngp_chol_large")
+            outs = o.cpu().numpy()
+        else:
+            rc = self.lib.cngp_chol_large(self.h, C.byref(k), a[0].ptr, a[1].ptr, a[2].ptr, N, outs.ctypes.data,
+                                          outs.ctypes.data + 8, outs.ctypes.data + 16, a[3].ptr, L.MEM_HOST)
+            self._check(rc, "cngp_chol_large")
+        res = dict(logdet=float(outs[0]), quad=float(outs[1]), lml=float(outs[2]))
+        if want_alpha:
+            res["alpha"] = alpha
+        return res

@@ -1,0 +1,531 @@
+// C-ABI entry points of libcngp (include/cngp.h): context, kernel-expression parsing, batched predict,
+// LML/gradient, look-ahead.  Host-side orchestration only; all arithmetic is in the kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gp_fit.cuh"
+#include "gp_grad.cuh"
+#include "gp_var.cuh"
+
+extern "C" int cngp_launch_lookahead(const double*, const double*, long long, int, const double*, const double*,
+                                     const double*, const double*, const double*, int, const cngp_stop_config*, int*,
+                                     int*, int*, double*, cudaStream_t);
+extern "C" int cngp_launch_llh_to_enu(const double*, long long, const cngp_stop_config*, double*, cudaStream_t);
+
+using namespace cngp;
+
+namespace {
+std::string g_create_error;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct cngp_ctx {
+  cngp_config cfg;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  double* scratch = nullptr;  // factors (L / W tiles) + z
+  size_t scratch_bytes = 0;
+  std::vector<DevBuf> bufs;   // grow-only staging for host-memory calls
+
+  void* buf(size_t slot, size_t bytes) {
+    if (bufs.size() <= slot) bufs.resize(slot + 1);
+    DevBuf& b = bufs[slot];
+    if (b.cap < bytes) {
+      if (b.p) cudaFree(b.p);
+      b.p = nullptr;
+      b.cap = 0;
+      if (cudaMalloc(&b.p, bytes) != cudaSuccess) return nullptr;
+      b.cap = bytes;
+    }
+    return b.p;
+  }
+};
+
+static int fail(cngp_ctx* c, int code, const char* fmt, ...) {
+  char tmp[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tmp, sizeof tmp, fmt, ap);
+  va_end(ap);
+  if (c) c->err = tmp; else g_create_error = tmp;
+  return code;
+}
+
+#define CU(c, call)                                                                                  \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) return fail(c, CNGP_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// kernel expressions
+// ------------------------------------------------------------------------------------------------------------
+static int leaf_from_name(const std::string& s) {
+  static const struct { const char* n; int t; } tab[] = {
+      {"rbf", CNGP_K_RBF}, {"se", CNGP_K_RBF}, {"mat32", CNGP_K_MAT32}, {"matern32", CNGP_K_MAT32},
+      {"mat52", CNGP_K_MAT52}, {"matern52", CNGP_K_MAT52}, {"ratquad", CNGP_K_RATQUAD}, {"rq", CNGP_K_RATQUAD},
+      {"stdperiodic", CNGP_K_STDPERIODIC}, {"periodic", CNGP_K_STDPERIODIC}, {"per", CNGP_K_STDPERIODIC},
+      {"brownian", CNGP_K_BROWNIAN}, {"linear", CNGP_K_LINEAR}, {"bias", CNGP_K_BIAS}, {"const", CNGP_K_BIAS},
+      {"white", CNGP_K_WHITE}};
+  for (auto& e : tab)
+    if (s == e.n) return e.t;
+  return 0;
+}
+
+extern "C" int cngp_kernel_finalize(cngp_kernel* k) {
+  if (!k || k->n_ops <= 0 || k->n_ops > CNGP_MAX_OPS) return CNGP_ERR_INVALID;
+  int depth = 0, np = 0;
+  for (int i = 0; i < k->n_ops; ++i) {
+    const int op = k->ops[i];
+    if (op >= CNGP_K_RBF && op <= CNGP_K_WHITE) {
+      ++depth;
+      np += leaf_nparams(op);
+    } else if (op == CNGP_OP_ADD || op == CNGP_OP_MUL) {
+      if (depth < 2) return CNGP_ERR_INVALID;
+      --depth;
+    } else {
+      return CNGP_ERR_INVALID;
+    }
+  }
+  if (depth != 1 || np > CNGP_MAX_PARAMS) return CNGP_ERR_INVALID;
+  k->n_params = np;
+  return CNGP_OK;
+}
+
+extern "C" int cngp_kernel_parse(const char* text, cngp_kernel* out) {
+  if (!text || !out) return CNGP_ERR_INVALID;
+  std::vector<int> outq;
+  std::vector<char> st;
+  std::string cur;
+  auto flush = [&]() -> bool {
+    if (cur.empty()) return true;
+    const int t = leaf_from_name(cur);
+    cur.clear();
+    if (!t) return false;
+    outq.push_back(t);
+    return true;
+  };
+  auto prec = [](char c) { return c == '+' ? 1 : 2; };
+  for (const char* p = text; *p; ++p) {
+    const char ch = (char)tolower((unsigned char)*p);
+    if (ch == ' ') continue;
+    if (ch == '+' || ch == '*') {
+      if (!flush()) return CNGP_ERR_INVALID;
+      while (!st.empty() && st.back() != '(' && prec(st.back()) >= prec(ch)) {
+        outq.push_back(st.back() == '+' ? CNGP_OP_ADD : CNGP_OP_MUL);
+        st.pop_back();
+      }
+      st.push_back(ch);
+    } else if (ch == '(') {
+      st.push_back(ch);
+    } else if (ch == ')') {
+      if (!flush()) return CNGP_ERR_INVALID;
+      while (!st.empty() && st.back() != '(') {
+        outq.push_back(st.back() == '+' ? CNGP_OP_ADD : CNGP_OP_MUL);
+        st.pop_back();
+      }
+      if (st.empty()) return CNGP_ERR_INVALID;
+      st.pop_back();
+    } else {
+      cur.push_back(ch);
+    }
+  }
+  if (!flush()) return CNGP_ERR_INVALID;
+  while (!st.empty()) {
+    if (st.back() == '(') return CNGP_ERR_INVALID;
+    outq.push_back(st.back() == '+' ? CNGP_OP_ADD : CNGP_OP_MUL);
+    st.pop_back();
+  }
+  if (outq.empty() || (int)outq.size() > CNGP_MAX_OPS) return CNGP_ERR_INVALID;
+  memset(out, 0, sizeof *out);
+  out->n_ops = (int)outq.size();
+  for (size_t i = 0; i < outq.size(); ++i) out->ops[i] = outq[i];
+  return cngp_kernel_finalize(out);
+}
+
+// postfix program -> sum of products of leaves
+static int build_kprog(const cngp_kernel* k, KProg* kp) {
+  cngp_kernel kk = *k;
+  if (cngp_kernel_finalize(&kk) != CNGP_OK) return CNGP_ERR_INVALID;
+  typedef std::vector<std::pair<int, int>> Term;  // (leaf type, param offset)
+  std::vector<std::vector<Term>> st;
+  int poff = 0;
+  for (int i = 0; i < kk.n_ops; ++i) {
+    const int op = kk.ops[i];
+    if (op < CNGP_OP_ADD) {
+      st.push_back({Term{{op, poff}}});
+      poff += leaf_nparams(op);
+    } else {
+      std::vector<Term> b = st.back(); st.pop_back();
+      std::vector<Term> a = st.back(); st.pop_back();
+      std::vector<Term> r;
+      if (op == CNGP_OP_ADD) {
+        r = a;
+        r.insert(r.end(), b.begin(), b.end());
+      } else {
+        for (auto& ta : a)
+          for (auto& tb : b) {
+            Term t = ta;
+            t.insert(t.end(), tb.begin(), tb.end());
+            r.push_back(t);
+          }
+      }
+      st.push_back(r);
+    }
+  }
+  memset(kp, 0, sizeof *kp);
+  int nl = 0;
+  kp->n_terms = (int)st.back().size();
+  if (kp->n_terms > CNGP_MAX_LEAVES) return CNGP_ERR_UNSUPPORTED;
+  for (int t = 0; t < kp->n_terms; ++t) {
+    kp->term_start[t] = nl;
+    for (auto& lf : st.back()[t]) {
+      if (nl >= CNGP_MAX_LEAVES) return CNGP_ERR_UNSUPPORTED;
+      kp->leaf_type[nl] = lf.first;
+      kp->leaf_param[nl] = lf.second;
+      ++nl;
+    }
+  }
+  kp->term_start[kp->n_terms] = nl;
+  kp->n_leaves = nl;
+  kp->n_params = kk.n_params;
+  kp->fast_id = 0;
+  return CNGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int cngp_version(void) { return CNGP_VERSION; }
+
+extern "C" void cngp_default_config(cngp_config* cfg) {
+  memset(cfg, 0, sizeof *cfg);
+  cfg->device = 0;
+  cfg->jitter_retry = 0;
+  cfg->scratch_bytes = 0;
+}
+
+extern "C" int cngp_create(const cngp_config* cfg, cngp_ctx** out) {
+  if (!out) return fail(nullptr, CNGP_ERR_INVALID, "cngp_create: out is null");
+  *out = nullptr;
+  cngp_config c;
+  if (cfg) c = *cfg; else cngp_default_config(&c);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, CNGP_ERR_CUDA, "cngp_create: no CUDA device (%s) - libcngp has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (c.device < 0 || c.device >= ndev) return fail(nullptr, CNGP_ERR_INVALID, "cngp_create: bad device %d", c.device);
+  CU(nullptr, cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  CU(nullptr, cudaGetDeviceProperties(&prop, c.device));
+  if (prop.major != 10)
+    return fail(nullptr, CNGP_ERR_UNSUPPORTED, "cngp_create: device %s is sm_%d%d; this library is built for sm_100a only",
+                prop.name, prop.major, prop.minor);
+  cngp_ctx* ctx = new cngp_ctx();
+  ctx->cfg = c;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, CNGP_ERR_CUDA, "cngp_create: cudaStreamCreate failed");
+  }
+  ctx->stream = ctx->own_stream;
+  ctx->scratch_bytes = c.scratch_bytes > 0 ? (size_t)c.scratch_bytes : ((size_t)2 << 30);
+  *out = ctx;
+  return CNGP_OK;
+}
+
+extern "C" void cngp_destroy(cngp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& b : ctx->bufs)
+    if (b.p) cudaFree(b.p);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" const char* cngp_last_error(cngp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int cngp_sync(cngp_ctx* ctx) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return CNGP_OK;
+}
+
+extern "C" int cngp_set_stream(cngp_ctx* ctx, void* s) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  return CNGP_OK;
+}
+
+extern "C" int64_t cngp_launch_count(cngp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static int ensure_scratch(cngp_ctx* ctx) {
+  if (ctx->scratch) return CNGP_OK;
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  cudaError_t e = cudaMalloc((void**)&ctx->scratch, ctx->scratch_bytes);
+  if (e != cudaSuccess) {
+    ctx->scratch = nullptr;
+    return fail(ctx, CNGP_ERR_NOMEM, "scratch allocation of %zu bytes failed: %s", ctx->scratch_bytes,
+                cudaGetErrorString(e));
+  }
+  return CNGP_OK;
+}
+
+// staging helpers for host-memory calls
+struct Stage {
+  cngp_ctx* ctx;
+  int mem;
+  size_t slot = 0;
+  int err = CNGP_OK;
+  struct Out { void* host; void* dev; size_t bytes; };
+  std::vector<Out> outs;
+  const void* in(const void* host, size_t bytes) {
+    if (!host || bytes == 0) return host;
+    if (mem == CNGP_MEM_DEVICE) return host;
+    void* d = ctx->buf(slot++, bytes);
+    if (!d) { err = CNGP_ERR_NOMEM; return nullptr; }
+    if (cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) err = CNGP_ERR_CUDA;
+    return d;
+  }
+  void* out(void* host, size_t bytes) {
+    if (!host || bytes == 0) return host;
+    if (mem == CNGP_MEM_DEVICE) return host;
+    void* d = ctx->buf(slot++, bytes);
+    if (!d) { err = CNGP_ERR_NOMEM; return nullptr; }
+    outs.push_back({host, d, bytes});
+    return d;
+  }
+  int finish() {
+    if (mem == CNGP_MEM_DEVICE) return err;
+    for (auto& o : outs)
+      if (cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) err = CNGP_ERR_CUDA;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) err = CNGP_ERR_CUDA;
+    return err;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// batched predict
+// ------------------------------------------------------------------------------------------------------------
+template <int NT_MAX, int WARPS>
+static void launch_var(const VarArgs& va, long long nwin, cudaStream_t s) {
+  const long long tasks = nwin * va.mt;
+  const long long grid = (tasks + WARPS - 1) / WARPS;
+  gp_var_kernel<NT_MAX, WARPS><<<(unsigned)grid, WARPS * 32, 0, s>>>(va);
+}
+
+extern "C" int cngp_predict_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t theta_stride,
+                                  const double* x, const double* y, const double* xstar, int64_t xstar_stride,
+                                  int64_t B, int32_t N, int32_t M, double* mean, double* var, double* lml,
+                                  int32_t* status, int32_t mem) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!kernel || !theta || !x || !y || B < 0 || N <= 0 || M < 0) return fail(ctx, CNGP_ERR_INVALID, "predict: bad argument");
+  if (M > 0 && (!xstar || !mean || !var)) return fail(ctx, CNGP_ERR_INVALID, "predict: xstar/mean/var null");
+  if (N > CNGP_MAX_N) return fail(ctx, CNGP_ERR_UNSUPPORTED, "predict: N=%d > %d (use cngp_chol_large)", N, CNGP_MAX_N);
+  if (B == 0) return CNGP_OK;
+  KProg kp;
+  int rc = build_kprog(kernel, &kp);
+  if (rc) return fail(ctx, rc, "predict: invalid kernel expression");
+  const int P = kp.n_params + 1;
+  if (theta_stride != 0 && theta_stride < P) return fail(ctx, CNGP_ERR_INVALID, "predict: theta_stride < n_params+1");
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  if ((rc = ensure_scratch(ctx))) return rc;
+
+  Stage st{ctx, mem};
+  const double* d_theta = (const double*)st.in(theta, sizeof(double) * (theta_stride ? (size_t)B * theta_stride : P));
+  const double* d_x = (const double*)st.in(x, sizeof(double) * (size_t)B * N);
+  const double* d_y = (const double*)st.in(y, sizeof(double) * (size_t)B * N);
+  const double* d_xs = M ? (const double*)st.in(xstar, sizeof(double) * (xstar_stride ? (size_t)B * xstar_stride : M)) : nullptr;
+  double* d_mean = M ? (double*)st.out(mean, sizeof(double) * (size_t)B * M) : nullptr;
+  double* d_var = M ? (double*)st.out(var, sizeof(double) * (size_t)B * M) : nullptr;
+  double* d_lml = (double*)st.out(lml, sizeof(double) * (size_t)B);
+  int* d_status = (int*)st.out(status, sizeof(int) * (size_t)B);
+  if (st.err) return fail(ctx, st.err, "predict: staging failed");
+  if (!d_status) {  // phase B needs the status to poison failed windows
+    d_status = (int*)ctx->buf(15, sizeof(int) * (size_t)B);
+    if (!d_status) return fail(ctx, CNGP_ERR_NOMEM, "predict: status buffer");
+  }
+
+  const int nt = (N + 7) / 8, mt = (M + 7) / 8;
+  const size_t per_problem = ((size_t)tiles_in_lower(nt) * 64 + (size_t)nt * 8) * sizeof(double);
+  const long long chunk = std::max<long long>(1, (long long)(ctx->scratch_bytes / per_problem));
+  for (long long w0 = 0; w0 < B; w0 += chunk) {
+    const long long nw = std::min<long long>(chunk, B - w0);
+    double* Lbuf = ctx->scratch;
+    double* zbuf = ctx->scratch + (size_t)nw * tiles_in_lower(nt) * 64;
+    FitArgs fa;
+    fa.kp = kp;
+    fa.theta = d_theta; fa.theta_stride = theta_stride; fa.theta_mode = theta_stride ? 1 : 0;
+    fa.x = d_x; fa.y = d_y; fa.N = N; fa.nt = nt; fa.n_windows = (int)B; fa.problem0 = w0;
+    fa.L = Lbuf; fa.z = zbuf; fa.lml = d_lml; fa.logdet = nullptr; fa.quad = nullptr; fa.status = d_status;
+    fa.jitter_retry = ctx->cfg.jitter_retry;
+    gp_fit_kernel<<<(unsigned)nw, FIT_THREADS, 0, ctx->stream>>>(fa);
+    ctx->launches++;
+    if (M > 0) {
+      VarArgs va;
+      va.kp = kp;
+      va.theta = d_theta; va.theta_stride = theta_stride; va.theta_mode = theta_stride ? 1 : 0;
+      va.x = d_x; va.xstar = d_xs; va.xstar_stride = xstar_stride;
+      va.N = N; va.nt = nt; va.M = M; va.mt = mt; va.window0 = w0; va.n_windows_launch = nw;
+      va.L = Lbuf; va.z = zbuf; va.status = d_status; va.mean = d_mean; va.var = d_var;
+      if (nt <= 8) launch_var<8, 8>(va, nw, ctx->stream);
+      else if (nt <= 16) launch_var<16, 8>(va, nw, ctx->stream);
+      else launch_var<32, 12>(va, nw, ctx->stream);
+      ctx->launches++;
+    }
+    CU(ctx, cudaGetLastError());
+  }
+  rc = st.finish();
+  if (rc) return fail(ctx, rc, "predict: copy-out failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return CNGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LML + gradient for C candidates x B windows
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int cngp_lml_grad_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t C,
+                                   const double* x, const double* y, int64_t B, int32_t N, double* lml, double* grad,
+                                   int32_t* status, int32_t mem) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!kernel || !theta || !x || !y || C < 0 || B < 0 || N <= 0) return fail(ctx, CNGP_ERR_INVALID, "lml_grad: bad argument");
+  if (N > CNGP_MAX_N) return fail(ctx, CNGP_ERR_UNSUPPORTED, "lml_grad: N=%d > %d", N, CNGP_MAX_N);
+  if (C == 0 || B == 0) return CNGP_OK;
+  KProg kp;
+  int rc = build_kprog(kernel, &kp);
+  if (rc) return fail(ctx, rc, "lml_grad: invalid kernel expression");
+  const int P = kp.n_params + 1;
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  if ((rc = ensure_scratch(ctx))) return rc;
+  const long long n_prob = (long long)C * B;
+
+  Stage st{ctx, mem};
+  const double* d_theta = (const double*)st.in(theta, sizeof(double) * (size_t)C * P);
+  const double* d_x = (const double*)st.in(x, sizeof(double) * (size_t)B * N);
+  const double* d_y = (const double*)st.in(y, sizeof(double) * (size_t)B * N);
+  double* d_lml = (double*)st.out(lml, sizeof(double) * (size_t)n_prob);
+  double* d_grad = (double*)st.out(grad, sizeof(double) * (size_t)n_prob * P);
+  int* d_status = (int*)st.out(status, sizeof(int) * (size_t)n_prob);
+  if (st.err) return fail(ctx, st.err, "lml_grad: staging failed");
+  if (!d_status) {
+    d_status = (int*)ctx->buf(15, sizeof(int) * (size_t)n_prob);
+    if (!d_status) return fail(ctx, CNGP_ERR_NOMEM, "lml_grad: status buffer");
+  }
+
+  const int nt = (N + 7) / 8;
+  const size_t ltiles = (size_t)tiles_in_lower(nt) * 64;
+  const size_t per_problem = (ltiles * (grad ? 2 : 1) + (size_t)nt * 8 * 2) * sizeof(double);
+  const long long chunk = std::max<long long>(1, (long long)(ctx->scratch_bytes / per_problem));
+  for (long long p0 = 0; p0 < n_prob; p0 += chunk) {
+    const long long np = std::min<long long>(chunk, n_prob - p0);
+    double* Lbuf = ctx->scratch;
+    double* Wbuf = Lbuf + (size_t)np * ltiles;
+    double* zbuf = grad ? Wbuf + (size_t)np * ltiles : Wbuf;
+    double* abuf = zbuf + (size_t)np * nt * 8;
+    FitArgs fa;
+    fa.kp = kp;
+    fa.theta = d_theta; fa.theta_stride = P; fa.theta_mode = 2;
+    fa.x = d_x; fa.y = d_y; fa.N = N; fa.nt = nt; fa.n_windows = (int)B; fa.problem0 = p0;
+    fa.L = Lbuf; fa.z = zbuf; fa.lml = d_lml; fa.logdet = nullptr; fa.quad = nullptr; fa.status = d_status;
+    fa.jitter_retry = ctx->cfg.jitter_retry;
+    gp_fit_kernel<<<(unsigned)np, FIT_THREADS, 0, ctx->stream>>>(fa);
+    ctx->launches++;
+    if (grad) {
+      GradArgs ga;
+      ga.kp = kp;
+      ga.theta = d_theta; ga.theta_stride = P;
+      ga.x = d_x; ga.N = N; ga.nt = nt; ga.n_windows = (int)B; ga.problem0 = p0;
+      ga.L = Lbuf; ga.W = Wbuf; ga.z = zbuf; ga.alpha = abuf; ga.status = d_status; ga.grad = d_grad;
+      gp_grad_kernel<<<(unsigned)np, GRAD_THREADS, 0, ctx->stream>>>(ga);
+      ctx->launches++;
+    }
+    CU(ctx, cudaGetLastError());
+  }
+  rc = st.finish();
+  if (rc) return fail(ctx, rc, "lml_grad: copy-out failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return CNGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// stop predictor
+// ------------------------------------------------------------------------------------------------------------
+extern "C" void cngp_default_stop_config(cngp_stop_config* c) {
+  c->v_nom = 0.8; c->floor_a = 0.03; c->floor_b = 0.05; c->track = 0.685; c->scale = 25.0; c->thresh = 3.0;
+  c->ratio = 5; c->fix_h_packing = 0;
+  c->init_llh[0] = 0.693457963620326; c->init_llh[1] = -1.39498384275845; c->init_llh[2] = 334.993517334743;
+  c->init_ecef[0] = 859153.015300000; c->init_ecef[1] = -4836303.72660000; c->init_ecef[2] = 4055378.50100000;
+}
+
+extern "C" int cngp_zupt_lookahead_batch(cngp_ctx* ctx, const double* mean, const double* sigma, int64_t B, int32_t M,
+                                         const double* P, const double* Q, const double* STM, const double* Hvec,
+                                         const double* pos, int32_t per_window, const cngp_stop_config* cfg,
+                                         int32_t* triggered, int32_t* i_stop, int32_t* step_stop, double* xy_err,
+                                         int32_t mem) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!mean || !sigma || !P || !Q || !STM || !Hvec || !pos || !triggered || !i_stop || B < 0 || M <= 0)
+    return fail(ctx, CNGP_ERR_INVALID, "lookahead: bad argument");
+  if (B == 0) return CNGP_OK;
+  cngp_stop_config c;
+  if (cfg) c = *cfg; else cngp_default_stop_config(&c);
+  if (c.ratio <= 0) return fail(ctx, CNGP_ERR_INVALID, "lookahead: ratio must be positive");
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  Stage st{ctx, mem};
+  auto cnt = [&](int bit, size_t sz) { return sizeof(double) * sz * ((per_window & bit) ? (size_t)B : 1); };
+  const double* d_mean = (const double*)st.in(mean, sizeof(double) * (size_t)B * M);
+  const double* d_sigma = (const double*)st.in(sigma, sizeof(double) * (size_t)B * M);
+  const double* d_P = (const double*)st.in(P, cnt(CNGP_PERWIN_P, 225));
+  const double* d_Q = (const double*)st.in(Q, cnt(CNGP_PERWIN_Q, 225));
+  const double* d_F = (const double*)st.in(STM, cnt(CNGP_PERWIN_STM, 225));
+  const double* d_H = (const double*)st.in(Hvec, cnt(CNGP_PERWIN_H, 60));
+  const double* d_pos = (const double*)st.in(pos, cnt(CNGP_PERWIN_POS, 3));
+  int* d_trig = (int*)st.out(triggered, sizeof(int) * (size_t)B);
+  int* d_i = (int*)st.out(i_stop, sizeof(int) * (size_t)B);
+  int* d_step = (int*)st.out(step_stop, sizeof(int) * (size_t)B);
+  double* d_xy = (double*)st.out(xy_err, sizeof(double) * (size_t)B);
+  if (st.err) return fail(ctx, st.err, "lookahead: staging failed");
+  if (!d_step) d_step = (int*)ctx->buf(14, sizeof(int) * (size_t)B);
+  if (!d_xy) d_xy = (double*)ctx->buf(13, sizeof(double) * (size_t)B);
+  if (!d_step || !d_xy) return fail(ctx, CNGP_ERR_NOMEM, "lookahead: buffers");
+  const int e = cngp_launch_lookahead(d_mean, d_sigma, B, M, d_P, d_Q, d_F, d_H, d_pos, per_window, &c, d_trig, d_i,
+                                      d_step, d_xy, ctx->stream);
+  ctx->launches++;
+  if (e) return fail(ctx, CNGP_ERR_CUDA, "lookahead launch: %s", cudaGetErrorString((cudaError_t)e));
+  const int rc = st.finish();
+  if (rc) return fail(ctx, rc, "lookahead: copy-out failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return CNGP_OK;
+}
+
+extern "C" int cngp_llh_to_enu(cngp_ctx* ctx, const double* llh, int64_t n, const cngp_stop_config* cfg, double* enu,
+                               int32_t mem) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!llh || !enu || n < 0) return fail(ctx, CNGP_ERR_INVALID, "llh_to_enu: bad argument");
+  if (n == 0) return CNGP_OK;
+  cngp_stop_config c;
+  if (cfg) c = *cfg; else cngp_default_stop_config(&c);
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  Stage st{ctx, mem};
+  const double* d_in = (const double*)st.in(llh, sizeof(double) * 3 * (size_t)n);
+  double* d_out = (double*)st.out(enu, sizeof(double) * 3 * (size_t)n);
+  if (st.err) return fail(ctx, st.err, "llh_to_enu: staging failed");
+  const int e = cngp_launch_llh_to_enu(d_in, n, &c, d_out, ctx->stream);
+  ctx->launches++;
+  if (e) return fail(ctx, CNGP_ERR_CUDA, "llh_to_enu launch: %s", cudaGetErrorString((cudaError_t)e));
+  const int rc = st.finish();
+  if (rc) return fail(ctx, rc, "llh_to_enu: copy-out failed");
+  return CNGP_OK;
+}

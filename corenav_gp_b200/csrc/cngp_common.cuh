@@ -1,0 +1,71 @@
+// Shared device/host definitions for the cngp kernels (sm_100a).
+//
+// Tile algebra used by every linear-algebra kernel here
+// -----------------------------------------------------
+// All matrices are cut into 8x8 FP64 tiles stored row-major (64 doubles = 512 B).  A warp holds a tile as two
+// doubles per lane: lane = 4*r + q  (r = lane>>2 row, q = lane&3)  holds  T[r][2q] and T[r][2q+1]  - which is both
+// the accumulator (C/D) fragment layout of  mma.sync.aligned.m8n8k4.f64  and exactly one 16-byte load per lane.
+// With the k index of the two k4-steps permuted (step s uses k = 2q+s), the same registers are also valid A and B
+// fragments, so   tile_mma(D, X, Y):  D += X * Y^T   needs no shuffle and no layout conversion:
+//     step s:  A[r][q] = X[r][2q+s],  B[q][n] = Y[n][2q+s]   =>   D[r][n] += sum_q X[r][2q+s] * Y[n][2q+s].
+// Cholesky, triangular solves (with explicitly inverted 8x8 diagonal tiles), L^-1, K^-1 = W^T W and the
+// predictive-variance substitution are all written as sequences of tile_mma, i.e. FP64 tensor-core DMMA.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/cngp.h"
+
+#define CNGP_JITTER 1e-8          // GPy exact_gaussian_inference.py: Ky = K + (sigma_n^2 + 1e-8) I
+#define CNGP_VAR_FLOOR 1e-15      // GPy posterior.py: np.clip(var, 1e-15, inf)
+#define CNGP_LOG_2PI 1.8378770664093454836
+
+namespace cngp {
+
+struct tile2 {
+  double a, b;  // T[r][2q], T[r][2q+1]
+};
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+
+// D += X * Y^T  (all three in the lane layout above)
+__device__ __forceinline__ void tile_mma(tile2& d, const tile2& x, const tile2& y) {
+  dmma884(d.a, d.b, x.a, y.a);
+  dmma884(d.a, d.b, x.b, y.b);
+}
+
+__device__ __forceinline__ tile2 tile_load(const double* tile, int lane) {
+  const double2 v = *reinterpret_cast<const double2*>(tile + 2 * lane);
+  return tile2{v.x, v.y};
+}
+__device__ __forceinline__ void tile_store(double* tile, int lane, const tile2& t) {
+  *reinterpret_cast<double2*>(tile + 2 * lane) = make_double2(t.a, t.b);
+}
+
+// Column-block-major packed lower-triangular tile storage, indexed from the LAST tile column so that offsets do not
+// depend on the number of tile rows nt:  column j (J = nt-1-j) starts at J(J+1)/2 tiles and holds tiles i = j..nt-1.
+__host__ __device__ __forceinline__ int tile_index(int i, int j, int nt) {
+  const int J = nt - 1 - j;
+  return J * (J + 1) / 2 + (i - j);
+}
+__host__ __device__ __forceinline__ int tiles_in_lower(int nt) { return nt * (nt + 1) / 2; }
+
+// ------------------------------------------------------------------------------------------------------------
+// covariance functions.  A kernel expression (postfix program, cngp.h) is expanded on the host into a sum of
+// products of leaves; the device evaluates   k = sum_t prod_u leaf_{t,u}.
+// ------------------------------------------------------------------------------------------------------------
+#define CNGP_MAX_LEAVES 24
+struct KProg {
+  int n_terms;
+  int n_leaves;                      // total leaves over all terms
+  int n_params;                      // kernel hyper-parameters (noise excluded)
+  int term_start[CNGP_MAX_LEAVES + 1];
+  int leaf_type[CNGP_MAX_LEAVES];    // CNGP_K_*
+  int leaf_param[CNGP_MAX_LEAVES];   // offset of the leaf's first hyper-parameter in theta
+  int fast_id;                       // 0 generic, else a specialised evaluator (see kernel_eval.cuh)
+};
+
+}  // namespace cngp

@@ -1,0 +1,185 @@
+// Gradient of the log marginal likelihood with respect to every hyper-parameter, for one (candidate, window)
+// problem per CTA, given the factor produced by gp_fit_kernel.
+//
+// Replaces what m.optimize() evaluates per objective call at core_navigation/script/gp_slip_node.py:36 (row a4):
+// GPy ExactGaussianInference (Ky^-1 by dpotri, dL_dK = 0.5 (alpha alpha' - Ky^-1), dL_dthetaL = trace(dL_dK)) and
+// kern.update_gradients_full(dL_dK, X) with the Add / Prod chain rules.
+//
+// Steps, all tile_mma (FP64 DMMA) on 8x8 tiles:
+//   1. W = L^-1 by tile columns, kept TRANSPOSED per tile (WT(i,j) = W_ij^T) so that every product stays in the
+//      X * Y^T form:  T^T = sum_{k=j}^{i-1} WT(k,j) L(i,k)^T,   WT(i,j) = -T^T inv(L_ii)^T.  Columns are independent
+//      and are dealt cyclically to the warps.
+//   2. alpha = W^T z as row tiles:  alpha_a = sum_{m>=a} z_m^T W_ma.
+//   3. Ky^-1 = W^T W one lower tile at a time, Kinv(a,b) = sum_{m>=a} WT(m,a) WT(m,b)^T, consumed immediately:
+//      each lane contracts its two entries of dL_dK with dK/dtheta (evaluated in registers) - Ky^-1 is never stored.
+#pragma once
+#include "kernel_eval.cuh"
+
+namespace cngp {
+
+constexpr int GRAD_WARPS = 8;
+constexpr int GRAD_THREADS = GRAD_WARPS * 32;
+
+struct GradArgs {
+  KProg kp;
+  const double* theta;     // [C][P]
+  long long theta_stride;  // P
+  const double* x;         // [n_windows][N]
+  int N, nt, n_windows;
+  long long problem0;
+  const double* L;         // [chunk][tiles][64]  from gp_fit_kernel (diag tiles hold inv(L_jj))
+  double* W;               // [chunk][tiles][64]  scratch: WT tiles
+  const double* z;         // [chunk][nt*8]
+  double* alpha;           // [chunk][nt*8] scratch / output
+  const int* status;       // [n_problems]
+  double* grad;            // [n_problems][P]
+};
+
+// tile^T in the lane layout: lane (r,q) gets T[2q][r], T[2q+1][r]
+__device__ __forceinline__ tile2 tile_load_T(const double* tile, int lane) {
+  const int r = lane >> 2, q = lane & 3;
+  return tile2{tile[(2 * q) * 8 + r], tile[(2 * q + 1) * 8 + r]};
+}
+
+__global__ void __launch_bounds__(GRAD_THREADS) gp_grad_kernel(const GradArgs a) {
+  __shared__ double xs[CNGP_MAX_N + 8];
+  __shared__ double al[CNGP_MAX_N + 8];
+  __shared__ double zs[CNGP_MAX_N + 8];
+  __shared__ double thv[CNGP_MAX_PARAMS + 1];
+  __shared__ double gred[GRAD_WARPS][CNGP_MAX_PARAMS + 1];
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int r = lane >> 2, q = lane & 3;
+  const long long lp = blockIdx.x;
+  const long long p = a.problem0 + lp;
+  const int win = (int)(p % a.n_windows);
+  const long long cand = p / a.n_windows;
+  const double* th = a.theta + cand * a.theta_stride;
+  const int N = a.N, nt = a.nt, P = a.kp.n_params + 1;
+  const double* Lp = a.L + lp * (long long)tiles_in_lower(nt) * 64;
+  double* Wp = a.W + lp * (long long)tiles_in_lower(nt) * 64;
+  const double* zp = a.z + lp * (long long)(nt * 8);
+
+  for (int i = tid; i < nt * 8; i += GRAD_THREADS) {
+    xs[i] = i < N ? a.x[(long long)win * N + i] : 0.0;
+    zs[i] = zp[i];
+  }
+  if (tid < P) thv[tid] = th[tid];
+  if (a.status[p] < 0) {  // factorisation failed: NaN gradient
+    if (tid < P) a.grad[p * P + tid] = __longlong_as_double(0x7ff8000000000000LL);
+    return;
+  }
+  __syncthreads();
+
+  // ---- 1. WT = (L^-1) tiles, column j on warp j % GRAD_WARPS ----
+  for (int j = w; j < nt; j += GRAD_WARPS) {
+    tile_store(Wp + (long long)tile_index(j, j, nt) * 64, lane, tile_load_T(Lp + (long long)tile_index(j, j, nt) * 64, lane));
+    __syncwarp();
+    for (int i = j + 1; i < nt; ++i) {
+      tile2 T0{0.0, 0.0}, T1{0.0, 0.0};
+      int k = j;
+      for (; k + 1 < i; k += 2) {
+        tile_mma(T0, tile_load(Wp + (long long)tile_index(k, j, nt) * 64, lane),
+                 tile_load(Lp + (long long)tile_index(i, k, nt) * 64, lane));
+        tile_mma(T1, tile_load(Wp + (long long)tile_index(k + 1, j, nt) * 64, lane),
+                 tile_load(Lp + (long long)tile_index(i, k + 1, nt) * 64, lane));
+      }
+      if (k < i)
+        tile_mma(T0, tile_load(Wp + (long long)tile_index(k, j, nt) * 64, lane),
+                 tile_load(Lp + (long long)tile_index(i, k, nt) * 64, lane));
+      const tile2 nT{-(T0.a + T1.a), -(T0.b + T1.b)};
+      tile2 Wt{0.0, 0.0};
+      tile_mma(Wt, nT, tile_load(Lp + (long long)tile_index(i, i, nt) * 64, lane));
+      tile_store(Wp + (long long)tile_index(i, j, nt) * 64, lane, Wt);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ---- 2. alpha_a = sum_{m>=a} z_m^T W_ma ----
+  for (int at = w; at < nt; at += GRAD_WARPS) {
+    tile2 acc{0.0, 0.0};
+    for (int m = at; m < nt; ++m) {
+      tile2 Z{0.0, 0.0};
+      if (r == 0) { Z.a = zs[8 * m + 2 * q]; Z.b = zs[8 * m + 2 * q + 1]; }
+      tile_mma(acc, Z, tile_load(Wp + (long long)tile_index(m, at, nt) * 64, lane));
+    }
+    if (r == 0) { al[8 * at + 2 * q] = acc.a; al[8 * at + 2 * q + 1] = acc.b; }
+  }
+  __syncthreads();
+  if (a.alpha)
+    for (int i = tid; i < nt * 8; i += GRAD_THREADS) a.alpha[lp * (long long)(nt * 8) + i] = al[i];
+
+  // ---- 3. Kinv tiles + contraction with dK/dtheta ----
+  double g[CNGP_MAX_PARAMS + 1];
+#pragma unroll
+  for (int i = 0; i <= CNGP_MAX_PARAMS; ++i) g[i] = 0.0;
+  const int n_tiles = tiles_in_lower(nt);
+  for (int t = w; t < n_tiles; t += GRAD_WARPS) {
+    // t -> (ta >= tb) by rows of the lower triangle
+    int ta = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((ta + 1) * (ta + 2) / 2 <= t) ++ta;
+    while (ta * (ta + 1) / 2 > t) --ta;
+    const int tb = t - ta * (ta + 1) / 2;
+    tile2 G0{0.0, 0.0}, G1{0.0, 0.0};
+    int m = ta;
+    for (; m + 1 < nt; m += 2) {
+      tile_mma(G0, tile_load(Wp + (long long)tile_index(m, ta, nt) * 64, lane),
+               tile_load(Wp + (long long)tile_index(m, tb, nt) * 64, lane));
+      tile_mma(G1, tile_load(Wp + (long long)tile_index(m + 1, ta, nt) * 64, lane),
+               tile_load(Wp + (long long)tile_index(m + 1, tb, nt) * 64, lane));
+    }
+    if (m < nt)
+      tile_mma(G0, tile_load(Wp + (long long)tile_index(m, ta, nt) * 64, lane),
+               tile_load(Wp + (long long)tile_index(m, tb, nt) * 64, lane));
+    const double kinv[2] = {G0.a + G1.a, G0.b + G1.b};
+    const double wsym = (ta == tb) ? 0.5 : 1.0;  // 0.5 * (2 for the mirrored off-diagonal tile)
+    const int row = 8 * ta + r;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = 8 * tb + 2 * q + e;
+      if (row < N && col < N) {
+        const double wgt = wsym * (al[row] * al[col] - kinv[e]);  // dL_dK entry (x2 when mirrored)
+        const bool same = row == col;
+        const double xa = xs[row], xb = xs[col];
+        double r2 = r2_expanded(xa, xb);
+        if (same) r2 = 0.0;
+        if (same) g[CNGP_MAX_PARAMS] += wgt;  // noise: trace(dL_dK)
+        for (int tt = 0; tt < a.kp.n_terms; ++tt) {
+          const int u0 = a.kp.term_start[tt], u1 = a.kp.term_start[tt + 1];
+          for (int u = u0; u < u1; ++u) {
+            double others = 1.0, dv[3];
+            for (int u2 = u0; u2 < u1; ++u2)
+              if (u2 != u)
+                others *= leaf_value_grad<true>(a.kp.leaf_type[u2], thv + a.kp.leaf_param[u2], xa, xb, r2, same, dv);
+            leaf_value_grad<true>(a.kp.leaf_type[u], thv + a.kp.leaf_param[u], xa, xb, r2, same, dv);
+            const int np = leaf_nparams(a.kp.leaf_type[u]);
+            const int po = a.kp.leaf_param[u];
+            const double ww = wgt * others;
+#pragma unroll
+            for (int i = 0; i < CNGP_MAX_PARAMS; ++i) {
+              const int jj = i - po;
+              if (jj >= 0 && jj < np) g[i] += ww * (jj == 0 ? dv[0] : (jj == 1 ? dv[1] : dv[2]));
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---- reduce over the CTA ----
+#pragma unroll
+  for (int i = 0; i <= CNGP_MAX_PARAMS; ++i) {
+    double v = g[i];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) gred[w][i] = v;
+  }
+  __syncthreads();
+  if (tid < P) {
+    const int src = (tid == P - 1) ? CNGP_MAX_PARAMS : tid;
+    double v = 0.0;
+    for (int ww = 0; ww < GRAD_WARPS; ++ww) v += gred[ww][src];
+    a.grad[p * P + tid] = v;
+  }
+}
+
+}  // namespace cngp

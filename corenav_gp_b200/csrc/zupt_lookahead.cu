@@ -1,0 +1,346 @@
+// Batched stop predictor: unscented transform of predicted slip -> odometry noise R_IP, 15-state covariance
+// look-ahead with a Joseph-form update every `ratio`-th step, and the 3-sigma horizontal error observer.
+//
+// Replaces the loop body of GpPredictor::GPCallBack, /root/reference/gp_predictor/src/gp_predictor.cpp:64-124
+// (rows a10-a12 of SURVEY.md section 8) and GpPredictor::llh_to_enu (:144-178), for B independent windows.
+// Reference quirks kept: H(r,c) = Hvec[r*4+c]; sigma is used as the sigma-point offset and the UT
+// covariance is squared again; update happens before the error check; only the +3 sigma point triggers.
+//
+// One warp per window; P and the temporaries live in shared memory, each lane owns up to 8 of the 225 outputs of a
+// 15x15 product and evaluates its dot products as ascending-index fma chains starting from 0 - the same operation
+// order as the C oracle, so (triggered, i) is reproducible bit for bit.  This translation unit is compiled with
+// -fmad=false: every fused operation below is an explicit fma().
+#include <cuda_runtime.h>
+#include "../../include/cngp.h"
+
+namespace cngp {
+
+constexpr int LA_WARPS = 4;
+
+struct LookaheadArgs {
+  const double* mean;   // [B][M]
+  const double* sigma;  // [B][M]
+  long long B;
+  int M;
+  const double* P; const double* Q; const double* STM; const double* Hvec; const double* pos;
+  int per_window;
+  cngp_stop_config cfg;
+  int* triggered; int* i_stop; int* step_stop; double* xy_err;
+};
+
+struct LlhConst {
+  double e2, one_m_e2;          // e*e, 1 - e*e with e = sqrt(1 - (b/a)^2)
+  double Rm[3][3];              // ECEF -> ENU rotation at init_llh
+};
+
+__device__ __forceinline__ LlhConst llh_prepare(const cngp_stop_config& c) {
+  LlhConst k;
+  const double a = 6378137.0000, b = 6356752.3142;
+  const double boa = b / a;
+  const double e = sqrt(1 - boa * boa);
+  k.e2 = e * e;
+  k.one_m_e2 = 1 - e * e;
+  const double sinPhi = sin(c.init_llh[0]), cosPhi = cos(c.init_llh[0]);
+  const double sinLam = sin(c.init_llh[1]), cosLam = cos(c.init_llh[1]);
+  k.Rm[0][0] = -1 * sinLam; k.Rm[0][1] = cosLam; k.Rm[0][2] = 0;
+  k.Rm[1][0] = (-1 * sinPhi) * cosLam; k.Rm[1][1] = (-1 * sinPhi) * sinLam; k.Rm[1][2] = cosPhi;
+  k.Rm[2][0] = cosPhi * cosLam; k.Rm[2][1] = cosPhi * sinLam; k.Rm[2][2] = sinPhi;
+  return k;
+}
+
+// gp_predictor.cpp:144-178 given the five trigonometric values of (lat, lon)
+__device__ __forceinline__ void llh_to_enu_trig(double sinphi, double cosphi, double tanphi, double sinlam, double coslam,
+                                                double h, const LlhConst& k, const cngp_stop_config& c, double enu[3]) {
+  const double a = 6378137.0000;
+  const double tan2phi = tanphi * tanphi;
+  const double tmpden = sqrt(1 + k.one_m_e2 * tan2phi);
+  const double x1 = (a * coslam) / tmpden + h * coslam * cosphi;
+  const double y1 = (a * sinlam) / tmpden + h * sinlam * cosphi;
+  const double tmp3 = sqrt(1 - k.e2 * sinphi * sinphi);
+  const double z1 = (a * k.one_m_e2 * sinphi) / tmp3 + h * sinphi;
+  const double d0 = x1 - c.init_ecef[0], d1 = y1 - c.init_ecef[1], d2 = z1 - c.init_ecef[2];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    double acc = 0.0;
+    acc = fma(k.Rm[r][0], d0, acc);
+    acc = fma(k.Rm[r][1], d1, acc);
+    acc = fma(k.Rm[r][2], d2, acc);
+    enu[r] = acc;
+  }
+}
+
+__device__ __forceinline__ void llh_to_enu_dev(double lat, double lon, double h, const LlhConst& k,
+                                               const cngp_stop_config& c, double enu[3]) {
+  llh_to_enu_trig(sin(lat), cos(lat), tan(lat), sin(lon), cos(lon), h, k, c, enu);
+}
+
+// closed-form 4x4 inverse through 2x2 minors (Eigen's fixed-size inverse at gp_predictor.cpp:90 is the same math)
+__device__ __forceinline__ void inv4(const double* m /*[16] row-major*/, double* o) {
+#define M_(r, c) m[(r) * 4 + (c)]
+  const double s0 = M_(0, 0) * M_(1, 1) - M_(1, 0) * M_(0, 1);
+  const double s1 = M_(0, 0) * M_(1, 2) - M_(1, 0) * M_(0, 2);
+  const double s2 = M_(0, 0) * M_(1, 3) - M_(1, 0) * M_(0, 3);
+  const double s3 = M_(0, 1) * M_(1, 2) - M_(1, 1) * M_(0, 2);
+  const double s4 = M_(0, 1) * M_(1, 3) - M_(1, 1) * M_(0, 3);
+  const double s5 = M_(0, 2) * M_(1, 3) - M_(1, 2) * M_(0, 3);
+  const double c5 = M_(2, 2) * M_(3, 3) - M_(3, 2) * M_(2, 3);
+  const double c4 = M_(2, 1) * M_(3, 3) - M_(3, 1) * M_(2, 3);
+  const double c3 = M_(2, 1) * M_(3, 2) - M_(3, 1) * M_(2, 2);
+  const double c2 = M_(2, 0) * M_(3, 3) - M_(3, 0) * M_(2, 3);
+  const double c1 = M_(2, 0) * M_(3, 2) - M_(3, 0) * M_(2, 2);
+  const double c0 = M_(2, 0) * M_(3, 1) - M_(3, 0) * M_(2, 1);
+  const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+  const double id = 1.0 / det;
+  o[0] = (M_(1, 1) * c5 - M_(1, 2) * c4 + M_(1, 3) * c3) * id;
+  o[1] = (-M_(0, 1) * c5 + M_(0, 2) * c4 - M_(0, 3) * c3) * id;
+  o[2] = (M_(3, 1) * s5 - M_(3, 2) * s4 + M_(3, 3) * s3) * id;
+  o[3] = (-M_(2, 1) * s5 + M_(2, 2) * s4 - M_(2, 3) * s3) * id;
+  o[4] = (-M_(1, 0) * c5 + M_(1, 2) * c2 - M_(1, 3) * c1) * id;
+  o[5] = (M_(0, 0) * c5 - M_(0, 2) * c2 + M_(0, 3) * c1) * id;
+  o[6] = (-M_(3, 0) * s5 + M_(3, 2) * s2 - M_(3, 3) * s1) * id;
+  o[7] = (M_(2, 0) * s5 - M_(2, 2) * s2 + M_(2, 3) * s1) * id;
+  o[8] = (M_(1, 0) * c4 - M_(1, 1) * c2 + M_(1, 3) * c0) * id;
+  o[9] = (-M_(0, 0) * c4 + M_(0, 1) * c2 - M_(0, 3) * c0) * id;
+  o[10] = (M_(3, 0) * s4 - M_(3, 1) * s2 + M_(3, 3) * s0) * id;
+  o[11] = (-M_(2, 0) * s4 + M_(2, 1) * s2 - M_(2, 3) * s0) * id;
+  o[12] = (-M_(1, 0) * c3 + M_(1, 1) * c1 - M_(1, 2) * c0) * id;
+  o[13] = (M_(0, 0) * c3 - M_(0, 1) * c1 + M_(0, 2) * c0) * id;
+  o[14] = (-M_(3, 0) * s3 + M_(3, 1) * s1 - M_(3, 2) * s0) * id;
+  o[15] = (M_(2, 0) * s3 - M_(2, 1) * s1 + M_(2, 2) * s0) * id;
+#undef M_
+}
+
+// gp_predictor.cpp:69-88
+__device__ __forceinline__ void ut_R(double mean, double sigma, const cngp_stop_config& c, double* R /*[16]*/) {
+  const double chi0 = c.v_nom / (1.0 - mean);
+  const double chi1 = c.v_nom / (1.0 - (mean + sigma));
+  const double chi2 = c.v_nom / (1.0 - (mean - sigma));
+  const double est = (chi0 + chi1 + chi2) / 3.0;
+  const double cov = ((chi0 - est) * (chi0 - est) + (chi1 - est) * (chi1 - est) + (chi2 - est) * (chi2 - est)) / 3.0;
+  const double c2 = cov * cov;
+  const double fa = c.floor_a * c.floor_a, fb = c.floor_b * c.floor_b;
+  const double R2[4] = {fmax(fa, c2), fmax(fa, c2), fmax(fb, c2), fb};
+  const double it = 1 / c.track;
+  const double R1[4][4] = {{0.5, 0.5, 0.0, 0.0}, {it, -it, 0.0, 0.0}, {0.0, 0.0, 1.0, 0.0}, {0.0, 0.0, 0.0, 1.0}};
+  double Bm[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) Bm[a][k] = (c.scale * R1[a][k]) * R2[k];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc = fma(Bm[a][k], R1[b][k], acc);
+      R[a * 4 + b] = acc;
+    }
+}
+
+// per-warp shared-memory working set (doubles)
+constexpr int LA_P = 0, LA_T = 225, LA_A = 450, LA_PHT = 675, LA_K = 735, LA_KR = 795, LA_S = 855, LA_SI = 871,
+              LA_R = 887, LA_F = 903, LA_Q = 1128, LA_H = 1353, LA_WS = 1413 + 3;  // padded to an even count
+
+__global__ void __launch_bounds__(LA_WARPS * 32) zupt_lookahead_kernel(const LookaheadArgs a) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long b = (long long)blockIdx.x * LA_WARPS + w;
+  if (b >= a.B) return;
+  double* ws = smem + (long long)w * LA_WS;
+  double *P = ws + LA_P, *T = ws + LA_T, *A = ws + LA_A, *PHt = ws + LA_PHT, *K = ws + LA_K, *KR = ws + LA_KR,
+         *S = ws + LA_S, *Si = ws + LA_SI, *R = ws + LA_R, *F = ws + LA_F, *Q = ws + LA_Q, *H = ws + LA_H;
+  const cngp_stop_config& cfg = a.cfg;
+  const int pw = a.per_window;
+  const double* gP = a.P + ((pw & CNGP_PERWIN_P) ? b * 225 : 0);
+  const double* gQ = a.Q + ((pw & CNGP_PERWIN_Q) ? b * 225 : 0);
+  const double* gF = a.STM + ((pw & CNGP_PERWIN_STM) ? b * 225 : 0);
+  const double* gH = a.Hvec + ((pw & CNGP_PERWIN_H) ? b * 60 : 0);
+  const double* gpos = a.pos + ((pw & CNGP_PERWIN_POS) ? b * 3 : 0);
+  for (int i = lane; i < 225; i += 32) { P[i] = gP[i]; Q[i] = gQ[i]; F[i] = gF[i]; }
+  for (int i = lane; i < 60; i += 32) {
+    const int rr = i / 15, cc = i % 15;
+    H[i] = gH[cfg.fix_h_packing ? rr * 15 + cc : rr * 4 + cc];  // gp_predictor.cpp:38-42 aliasing index
+  }
+  const double lat = gpos[0], lon = gpos[1], hgt = gpos[2];
+  const LlhConst lk = llh_prepare(cfg);
+  double enu0[3];
+  llh_to_enu_dev(lat, lon, hgt, lk, cfg, enu0);
+  __syncwarp();
+
+  const double* mean = a.mean + b * a.M;
+  const double* sigma = a.sigma + b * a.M;
+  const int nsteps = cfg.ratio * a.M;
+  int i_upd = 0, trig = 0, step = nsteps;
+  double xy = 0.0;
+
+  for (int slip_i = 0; slip_i < nsteps; ++slip_i) {
+    // ---- P = F P F' + Q ----
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int idx = lane + 32 * t;
+      if (idx < 225) {
+        const int rr = idx / 15, kk = idx % 15;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 15; ++j) acc = fma(F[rr * 15 + j], P[j * 15 + kk], acc);
+        T[idx] = acc;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int idx = lane + 32 * t;
+      if (idx < 225) {
+        const int rr = idx / 15, cc = idx % 15;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 15; ++k) acc = fma(T[rr * 15 + k], F[cc * 15 + k], acc);
+        P[idx] = acc + Q[idx];
+      }
+    }
+    __syncwarp();
+    if (slip_i % cfg.ratio == 0) {
+      // ---- UT -> R_IP, K = P H' (H P H' + R)^-1, Joseph update ----
+      double Rl[16];
+      ut_R(mean[i_upd], sigma[i_upd], cfg, Rl);
+      if (lane < 16) R[lane] = Rl[lane];
+      for (int idx = lane; idx < 60; idx += 32) {
+        const int rr = idx / 4, mm = idx % 4;
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 15; ++c) acc = fma(P[rr * 15 + c], H[mm * 15 + c], acc);
+        PHt[idx] = acc;
+      }
+      __syncwarp();
+      if (lane < 16) {
+        const int mm = lane / 4, nn = lane % 4;
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 15; ++c) acc = fma(H[mm * 15 + c], PHt[c * 4 + nn], acc);
+        S[lane] = acc + R[lane];
+      }
+      __syncwarp();
+      {
+        double Sl[16], Sil[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) Sl[e] = S[e];
+        inv4(Sl, Sil);
+        if (lane < 16) Si[lane] = Sil[lane];
+      }
+      __syncwarp();
+      for (int idx = lane; idx < 60; idx += 32) {
+        const int rr = idx / 4, mm = idx % 4;
+        double acc = 0.0;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc = fma(PHt[rr * 4 + n], Si[n * 4 + mm], acc);
+        K[idx] = acc;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int idx = lane + 32 * t;
+        if (idx < 225) {
+          const int rr = idx / 15, cc = idx % 15;
+          double acc = 0.0;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) acc = fma(K[rr * 4 + m], H[m * 15 + cc], acc);
+          A[idx] = (rr == cc ? 1.0 : 0.0) - acc;
+        }
+      }
+      for (int idx = lane; idx < 60; idx += 32) {
+        const int rr = idx / 4, nn = idx % 4;
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) acc = fma(K[rr * 4 + m], R[m * 4 + nn], acc);
+        KR[idx] = acc;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int idx = lane + 32 * t;
+        if (idx < 225) {
+          const int rr = idx / 15, kk = idx % 15;
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j < 15; ++j) acc = fma(A[rr * 15 + j], P[j * 15 + kk], acc);
+          T[idx] = acc;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int idx = lane + 32 * t;
+        if (idx < 225) {
+          const int rr = idx / 15, cc = idx % 15;
+          double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+          for (int k = 0; k < 15; ++k) a1 = fma(T[rr * 15 + k], A[cc * 15 + k], a1);
+#pragma unroll
+          for (int n = 0; n < 4; ++n) a2 = fma(KR[rr * 4 + n], K[cc * 4 + n], a2);
+          P[idx] = a1 + a2;
+        }
+      }
+      __syncwarp();
+      ++i_upd;
+    }
+    // ---- error observer: the five trigonometric values are spread over lanes 0..4 ----
+    const double lat3 = lat + 3.0 * sqrt(fabs(P[6 * 15 + 6]));
+    const double lon3 = lon + 3.0 * sqrt(fabs(P[7 * 15 + 7]));
+    const double h3 = hgt + 3.0 * sqrt(fabs(P[8 * 15 + 8]));
+    double tv = 0.0;
+    if (lane == 0) tv = sin(lat3);
+    else if (lane == 1) tv = cos(lat3);
+    else if (lane == 2) tv = tan(lat3);
+    else if (lane == 3) tv = sin(lon3);
+    else if (lane == 4) tv = cos(lon3);
+    const double sp = __shfl_sync(0xffffffffu, tv, 0), cp = __shfl_sync(0xffffffffu, tv, 1),
+                 tp = __shfl_sync(0xffffffffu, tv, 2), sl = __shfl_sync(0xffffffffu, tv, 3),
+                 cl = __shfl_sync(0xffffffffu, tv, 4);
+    double enu3[3];
+    llh_to_enu_trig(sp, cp, tp, sl, cl, h3, lk, cfg, enu3);
+    const double dx = enu3[0] - enu0[0], dy = enu3[1] - enu0[1];
+    xy = sqrt(dx * dx + dy * dy);
+    if (xy > cfg.thresh) { trig = 1; step = slip_i; break; }
+  }
+  if (lane == 0) {
+    a.triggered[b] = trig;
+    a.i_stop[b] = i_upd;
+    a.step_stop[b] = step;
+    a.xy_err[b] = xy;
+  }
+}
+
+__global__ void llh_to_enu_kernel(const double* llh, long long n, cngp_stop_config cfg, double* enu) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const LlhConst lk = llh_prepare(cfg);
+  double e[3];
+  llh_to_enu_dev(llh[3 * i], llh[3 * i + 1], llh[3 * i + 2], lk, cfg, e);
+  enu[3 * i] = e[0]; enu[3 * i + 1] = e[1]; enu[3 * i + 2] = e[2];
+}
+
+}  // namespace cngp
+
+extern "C" int cngp_launch_lookahead(const double* mean, const double* sigma, long long B, int M, const double* P,
+                                     const double* Q, const double* STM, const double* Hvec, const double* pos,
+                                     int per_window, const cngp_stop_config* cfg, int* triggered, int* i_stop,
+                                     int* step_stop, double* xy_err, cudaStream_t stream) {
+  using namespace cngp;
+  LookaheadArgs a{mean, sigma, B, M, P, Q, STM, Hvec, pos, per_window, *cfg, triggered, i_stop, step_stop, xy_err};
+  const size_t smem = (size_t)LA_WARPS * LA_WS * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(zupt_lookahead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  const long long grid = (B + LA_WARPS - 1) / LA_WARPS;
+  zupt_lookahead_kernel<<<(unsigned)grid, LA_WARPS * 32, smem, stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int cngp_launch_llh_to_enu(const double* llh, long long n, const cngp_stop_config* cfg, double* enu,
+                                      cudaStream_t stream) {
+  cngp::llh_to_enu_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(llh, n, *cfg, enu);
+  return (int)cudaGetLastError();
+}

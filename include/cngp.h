@@ -1,0 +1,181 @@
+/* cngp.h - C ABI of the B200-native GP slip-prediction hot path (corenav-GP).
+ *
+ * This is the drop-in boundary.  The reference has no FFI for this path - it crosses two
+ * ROS topics and one service - so each entry point below names the reference interface it replaces:
+ *
+ *   cngp_predict_batch          replaces GPy's GPRegression build + m.predict() loop as called from
+ *                               core_navigation/script/gp_slip_node.py:35,47-50 (rows a3, a6), for B windows at once
+ *   cngp_lml_grad_batch         replaces the objective/gradient evaluation inside m.optimize(),
+ *                               gp_slip_node.py:36 (rows a3, a4), for C hyper-parameter candidates x B windows
+ *   cngp_optimize_batch         replaces m.optimize() itself (gp_slip_node.py:36; paramz L-BFGS-B on softplus hypers)
+ *   cngp_gp_slip_batch          replaces the whole callback gp_slip_node.py:16-63 (rows a1-a7): train split,
+ *                               prediction grid, predict, mean[n:], sigma = 2 sqrt(var[n:])
+ *   cngp_zupt_lookahead_batch   replaces the loop of GpPredictor::GPCallBack, gp_predictor/src/gp_predictor.cpp:58-130
+ *                               (rows a9-a12), with the SetStopping response (core_navigation/srv/SetStopping.srv:1-7,
+ *                               CoreNav.cpp:652-676) passed as plain arrays
+ *   cngp_llh_to_enu             replaces GpPredictor::llh_to_enu, gp_predictor.cpp:144-178
+ *   cngp_chol_large*            the N = 32768 single-window factorisation of BASELINE.json configs[4] (same math as a3)
+ *
+ * Conventions: plain C, int status returns (0 = ok, negative = error; text via cngp_last_error), no exceptions
+ * cross the ABI, caller-owned buffers, row-major, FP64.  Every array argument is either a HOST pointer or a DEVICE
+ * pointer according to the `mem` argument of the call (CNGP_MEM_HOST / CNGP_MEM_DEVICE); host calls copy in and
+ * out through the context's pinned staging area and return after the results are in the caller's buffers; device
+ * calls are stream-ordered on the context's stream and return immediately (use cngp_sync).  One context per GPU;
+ * a context is not thread-safe.  There is NO CPU fallback: without a CUDA device cngp_create fails.
+ */
+#ifndef CNGP_H_
+#define CNGP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNGP_VERSION 100
+
+/* ---- status codes ---- */
+#define CNGP_OK 0
+#define CNGP_ERR_INVALID (-1)     /* bad argument */
+#define CNGP_ERR_CUDA (-2)        /* CUDA runtime error, see cngp_last_error */
+#define CNGP_ERR_UNSUPPORTED (-3) /* shape outside what the kernels cover */
+#define CNGP_ERR_NOMEM (-4)
+
+/* ---- memory space of the array arguments of a call ---- */
+#define CNGP_MEM_HOST 0
+#define CNGP_MEM_DEVICE 1
+
+/* ---- kernel families (GPy names; gp_slip_node.py:31-34, "Kernel Selection/README.md":18-20) ---- */
+#define CNGP_K_RBF 1         /* variance, lengthscale            sigma^2 exp(-r^2/2) */
+#define CNGP_K_MAT32 2       /* variance, lengthscale */
+#define CNGP_K_MAT52 3       /* variance, lengthscale */
+#define CNGP_K_RATQUAD 4     /* variance, lengthscale, power     sigma^2 (1 + r^2/2)^-power */
+#define CNGP_K_STDPERIODIC 5 /* variance, period, lengthscale    sigma^2 exp(-0.5 (sin(pi d/p)/l)^2) */
+#define CNGP_K_BROWNIAN 6    /* variance */
+#define CNGP_K_LINEAR 7      /* variance */
+#define CNGP_K_BIAS 8        /* variance */
+#define CNGP_K_WHITE 9       /* variance */
+#define CNGP_OP_ADD 16
+#define CNGP_OP_MUL 17
+#define CNGP_MAX_OPS 32      /* postfix program length */
+#define CNGP_MAX_PARAMS 24   /* kernel hyper-parameters (noise excluded) */
+#define CNGP_MAX_N 256       /* batched windows: training points per window */
+
+/* A composite covariance as a postfix program over the families above, e.g. "rbf*brownian" ->
+ * {RBF, BROWNIAN, MUL}.  theta of a window = the leaf hyper-parameters in program order followed by the Gaussian
+ * noise variance, so theta has n_params + 1 entries. */
+typedef struct cngp_kernel {
+  int32_t n_ops;
+  int32_t ops[CNGP_MAX_OPS];
+  int32_t n_params; /* filled by cngp_kernel_parse / cngp_kernel_finalize */
+} cngp_kernel;
+
+/* Parse "rbf*brownian", "se+periodic", "(rbf+linear)*brownian+white" ... (names as in the oracle / GPy). */
+int cngp_kernel_parse(const char* text, cngp_kernel* out);
+/* Validate a hand-filled program and compute n_params. */
+int cngp_kernel_finalize(cngp_kernel* k);
+
+typedef struct cngp_ctx cngp_ctx;
+
+typedef struct cngp_config {
+  int32_t device;            /* CUDA device ordinal */
+  int32_t jitter_retry;      /* 0: a non-PD window gets status < 0 and NaN outputs; 1: GPy jitchol ladder
+                                (mean(diag)*1e-6, x10, 5 tries) - status = tries used */
+  int64_t scratch_bytes;     /* device scratch for factors (0 = default 2 GiB); windows are processed in chunks */
+  int32_t reserved[8];
+} cngp_config;
+
+void cngp_default_config(cngp_config* cfg);
+int cngp_create(const cngp_config* cfg, cngp_ctx** out);
+void cngp_destroy(cngp_ctx* ctx);
+const char* cngp_last_error(cngp_ctx* ctx); /* ctx may be NULL: last create error */
+int cngp_sync(cngp_ctx* ctx);
+/* Make the context launch on an existing cudaStream_t (e.g. torch's current stream); NULL = the context's own. */
+int cngp_set_stream(cngp_ctx* ctx, void* cuda_stream);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t cngp_launch_count(cngp_ctx* ctx);
+int cngp_version(void);
+
+/* Exact-GP prediction for B independent windows (rows a3 + a6).
+ *   theta   [B][P] (theta_stride = P) or one shared vector (theta_stride = 0); P = kernel->n_params + 1, noise last
+ *   x, y    [B][N] training inputs / targets
+ *   xstar   [B][M] (xstar_stride = M) or shared [M] (xstar_stride = 0)
+ *   mean    [B][M]  K*' alpha
+ *   var     [B][M]  max(k** - sum V^2, 1e-15) + noise   (GPy predict, include_likelihood=True)
+ *   lml     [B]     log marginal likelihood (may be NULL)
+ *   status  [B]     0 ok; k > 0: jitter tries that were needed (jitter_retry=1); -k: factorisation failed at pivot k
+ *                   (1-based) - mean/var/lml of that window are NaN; (may be NULL)
+ */
+int cngp_predict_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t theta_stride,
+                       const double* x, const double* y, const double* xstar, int64_t xstar_stride,
+                       int64_t B, int32_t N, int32_t M,
+                       double* mean, double* var, double* lml, int32_t* status, int32_t mem);
+
+/* Log marginal likelihood and its gradient for C candidates x B windows (rows a3 + a4).
+ *   theta [C][P]; x, y [B][N]; lml [C][B]; grad [C][B][P] (d LML / d theta, noise last; may be NULL); status [C][B] */
+int cngp_lml_grad_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t C,
+                        const double* x, const double* y, int64_t B, int32_t N,
+                        double* lml, double* grad, int32_t* status, int32_t mem);
+
+/* Batched hyper-parameter fit (row a4): L-BFGS (history 10) on softplus-transformed [theta, noise] from theta0,
+ * one independent optimiser per window, objective/gradient on the GPU.  theta0 [B][P] or shared (stride 0);
+ * theta_out [B][P]; lml_out [B]; iters_out [B] (may be NULL).  HOST memory only. */
+int cngp_optimize_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta0, int64_t theta0_stride,
+                        const double* x, const double* y, int64_t B, int32_t N, int32_t max_iters,
+                        double* theta_out, double* lml_out, int32_t* iters_out);
+
+/* The node callback for B windows of n samples each (rows a1-a7): train on the first int(0.9 n) samples, predict on
+ * arange(min(time), max(time) + horizon, 1), keep entries [n:], sigma = 2 sqrt(var).  m_out = number of kept points
+ * per window (must be equal across the batch: same n and same ceil(span)); mean/sigma [B][m_cap].  theta [B][P] or
+ * shared; pass theta = NULL to fit the hypers first (cngp_optimize_batch from all-ones, as GPy does). HOST memory. */
+int cngp_gp_slip_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t theta_stride,
+                       const double* time_array, const double* slip_array, int64_t B, int32_t n,
+                       int32_t horizon, int32_t m_cap, double* mean, double* sigma, int32_t* m_out, int32_t* status);
+
+/* ---- stop predictor ---- */
+typedef struct cngp_stop_config {
+  double v_nom;      /* 0.8    gp_predictor.cpp:73-75 */
+  double floor_a;    /* 0.03   :80-81 */
+  double floor_b;    /* 0.05   :82-83 */
+  double track;      /* 0.685  :85 */
+  double scale;      /* 25     :88 */
+  double thresh;     /* 3.00   :102 */
+  int32_t ratio;     /* 5      :64,67 */
+  int32_t fix_h_packing; /* 0 = reference behaviour: H(r,c) = Hvec[r*4+c] (gp_predictor.cpp:38-42) */
+  double init_llh[3];    /* core_navigation/config/init_params.yaml:13-16 */
+  double init_ecef[3];   /* core_navigation/config/init_params.yaml:9-12 */
+} cngp_stop_config;
+
+void cngp_default_stop_config(cngp_stop_config* c);
+
+/* which context arrays carry one entry per window (else shared by the batch) */
+#define CNGP_PERWIN_P 1
+#define CNGP_PERWIN_Q 2
+#define CNGP_PERWIN_STM 4
+#define CNGP_PERWIN_H 8
+#define CNGP_PERWIN_POS 16
+
+/* Covariance look-ahead + 3-sigma error observer for B windows (rows a9-a12).
+ *   mean, sigma [B][M] (GP_Output); P, Q, STM [.][225] row-major 15x15; Hvec [.][60]; pos [.][3] (lat, lon, h)
+ *   triggered [B] 0/1; i_stop [B] = odometry updates performed when the loop ended (the reference's `i`);
+ *   step_stop [B] = slip_i at the trigger or ratio*M; xy_err [B] = last horizontal error computed. */
+int cngp_zupt_lookahead_batch(cngp_ctx* ctx, const double* mean, const double* sigma, int64_t B, int32_t M,
+                              const double* P, const double* Q, const double* STM, const double* Hvec,
+                              const double* pos, int32_t per_window, const cngp_stop_config* cfg,
+                              int32_t* triggered, int32_t* i_stop, int32_t* step_stop, double* xy_err, int32_t mem);
+
+/* GpPredictor::llh_to_enu for n points on the device (lat, lon, h -> E, N, U); llh, enu [n][3]. */
+int cngp_llh_to_enu(cngp_ctx* ctx, const double* llh, int64_t n, const cngp_stop_config* cfg, double* enu, int32_t mem);
+
+/* ---- large single window (BASELINE.json configs[4]) ----
+ * Blocked right-looking FP64 Cholesky of Ky = K(x,x) + (noise + 1e-8) I assembled on the device; returns
+ * logdet, y' Ky^-1 y and lml; alpha [N] (may be NULL).  Single GPU; the multi-GPU block-cyclic driver lives in
+ * corenav_gp_b200/large.py on top of cngp_chol_large_* panel primitives. */
+int cngp_chol_large(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, const double* x, const double* y,
+                    int64_t N, double* logdet, double* quad, double* lml, double* alpha, int32_t mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNGP_H_ */
