@@ -12,6 +12,7 @@ MAX_OPS = 32
 MAX_PARAMS = 24
 MAX_N = 256
 MEM_HOST, MEM_DEVICE = 0, 1
+PROF_FIT, PROF_VAR, PROF_GRAD, PROF_LOOKAHEAD, PROF_LARGE, PROF_MISC = range(6)
 PERWIN_P, PERWIN_Q, PERWIN_STM, PERWIN_H, PERWIN_POS = 1, 2, 4, 8, 16
 
 c_i32, c_i64, c_dp, c_ip, c_vp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p
@@ -41,8 +42,10 @@ SIGNATURES = {
     "cngp_destroy": (None, [c_vp]),
     "cngp_last_error": (C.c_char_p, [c_vp]),
     "cngp_sync": (C.c_int, [c_vp]),
-    "cngp_set_stream": (C.c_int, [c_vp, c_vp]),
+    "cngp_set_stream": (C.c_int, [c_vp, c_vp, c_i32]),
     "cngp_launch_count": (c_i64, [c_vp]),
+    "cngp_set_profiling": (C.c_int, [c_vp, c_i32]),
+    "cngp_profile_read": (C.c_int, [c_vp, c_i32, C.POINTER(C.c_double), C.POINTER(c_i64), c_i32]),
     "cngp_predict_batch": (C.c_int, [c_vp, C.POINTER(Kernel), c_dp, c_i64, c_dp, c_dp, c_dp, c_i64, c_i64, c_i32,
                                      c_i32, c_dp, c_dp, c_dp, c_ip, c_i32]),
     "cngp_lml_grad_batch": (C.c_int, [c_vp, C.POINTER(Kernel), c_dp, c_i64, c_dp, c_dp, c_i64, c_i32, c_dp, c_dp,

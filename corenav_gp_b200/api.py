@@ -104,11 +104,21 @@ class GpContext:
     def launch_count(self) -> int:
         return int(self.lib.cngp_launch_count(self.h))
 
+    def set_profiling(self, on: bool):
+        self._check(self.lib.cngp_set_profiling(self.h, int(on)), "cngp_set_profiling")
+
+    def profile_read(self, kernel_id: int, reset: bool = True):
+        """(total milliseconds, launches) of one kernel class since the last reset (CUDA events, launching stream)."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        self._check(self.lib.cngp_profile_read(self.h, kernel_id, C.byref(ms), C.byref(n), int(reset)),
+                    "cngp_profile_read")
+        return ms.value, n.value
+
     def _bind_stream(self, device_mode: bool):
         if device_mode:
-            self.lib.cngp_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+            self.lib.cngp_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream), 0)
         else:
-            self.lib.cngp_set_stream(self.h, None)
+            self.lib.cngp_set_stream(self.h, None, 1)
 
     def _empty(self, shape, dtype, device_mode, like=None):
         if device_mode:

@@ -24,6 +24,7 @@ using namespace cngp;
 
 namespace {
 std::string g_create_error;
+int g_sm_count = 148;
 }
 
 struct DevBuf {
@@ -40,6 +41,41 @@ struct cngp_ctx {
   double* scratch = nullptr;  // factors (L / W tiles) + z
   size_t scratch_bytes = 0;
   std::vector<DevBuf> bufs;   // grow-only staging for host-memory calls
+  // optional per-kernel timing with CUDA events on the launching stream (cngp_set_profiling)
+  bool profiling = false;
+  struct Span { int id; cudaEvent_t e0, e1; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
+  double prof_ms[CNGP_PROF_KERNELS] = {0};
+  long long prof_n[CNGP_PROF_KERNELS] = {0};
+
+  cudaEvent_t get_event() {
+    if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void begin(int id) {
+    launches++;
+    if (!profiling) return;
+    Span sp{id, get_event(), get_event()};
+    cudaEventRecord(sp.e0, stream);
+    spans.push_back(sp);
+  }
+  void end() {
+    if (!profiling) return;
+    cudaEventRecord(spans.back().e1, stream);
+  }
+  void collect() {
+    for (auto& sp : spans) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(sp.e1) == cudaSuccess && cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) {
+        prof_ms[sp.id] += ms;
+        prof_n[sp.id]++;
+      }
+      event_pool.push_back(sp.e0);
+      event_pool.push_back(sp.e1);
+    }
+    spans.clear();
+  }
 
   void* buf(size_t slot, size_t bytes) {
     if (bufs.size() <= slot) bufs.resize(slot + 1);
@@ -236,6 +272,7 @@ extern "C" int cngp_create(const cngp_config* cfg, cngp_ctx** out) {
   if (prop.major != 10)
     return fail(nullptr, CNGP_ERR_UNSUPPORTED, "cngp_create: device %s is sm_%d%d; this library is built for sm_100a only",
                 prop.name, prop.major, prop.minor);
+  g_sm_count = prop.multiProcessorCount;
   cngp_ctx* ctx = new cngp_ctx();
   ctx->cfg = c;
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -252,6 +289,8 @@ extern "C" void cngp_destroy(cngp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   cudaStreamSynchronize(ctx->stream);
+  ctx->collect();
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
   for (auto& b : ctx->bufs)
     if (b.p) cudaFree(b.p);
   if (ctx->scratch) cudaFree(ctx->scratch);
@@ -267,13 +306,30 @@ extern "C" int cngp_sync(cngp_ctx* ctx) {
   return CNGP_OK;
 }
 
-extern "C" int cngp_set_stream(cngp_ctx* ctx, void* s) {
+extern "C" int cngp_set_stream(cngp_ctx* ctx, void* s, int32_t use_own) {
   if (!ctx) return CNGP_ERR_INVALID;
-  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  ctx->collect();
+  ctx->stream = use_own ? ctx->own_stream : (cudaStream_t)s;  // s == 0 is the legacy default stream
   return CNGP_OK;
 }
 
 extern "C" int64_t cngp_launch_count(cngp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int cngp_set_profiling(cngp_ctx* ctx, int32_t on) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  ctx->collect();
+  ctx->profiling = on != 0;
+  return CNGP_OK;
+}
+
+extern "C" int cngp_profile_read(cngp_ctx* ctx, int32_t kernel_id, double* total_ms, int64_t* launches, int32_t reset) {
+  if (!ctx || kernel_id < 0 || kernel_id >= CNGP_PROF_KERNELS) return CNGP_ERR_INVALID;
+  ctx->collect();
+  if (total_ms) *total_ms = ctx->prof_ms[kernel_id];
+  if (launches) *launches = ctx->prof_n[kernel_id];
+  if (reset) { ctx->prof_ms[kernel_id] = 0.0; ctx->prof_n[kernel_id] = 0; }
+  return CNGP_OK;
+}
 
 static int ensure_scratch(cngp_ctx* ctx) {
   if (ctx->scratch) return CNGP_OK;
@@ -323,11 +379,33 @@ struct Stage {
 // ------------------------------------------------------------------------------------------------------------
 // batched predict
 // ------------------------------------------------------------------------------------------------------------
+template <int NT_MAX, int WARPS, int KID>
+static void launch_var_k(const VarArgs& va, long long nwin, cudaStream_t s) {
+  const long long grid = std::min<long long>(nwin, g_sm_count);   // persistent: one CTA per SM
+  const size_t smem = var_smem_bytes(WARPS);
+  static bool attr_done = false;   // one process per GPU: per-instantiation, set once
+  if (!attr_done) {
+    cudaFuncSetAttribute(gp_var_kernel<NT_MAX, WARPS, KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  gp_var_kernel<NT_MAX, WARPS, KID><<<(unsigned)grid, WARPS * 32, smem, s>>>(va);
+}
 template <int NT_MAX, int WARPS>
-static void launch_var(const VarArgs& va, long long nwin, cudaStream_t s) {
-  const long long tasks = nwin * va.mt;
-  const long long grid = (tasks + WARPS - 1) / WARPS;
-  gp_var_kernel<NT_MAX, WARPS><<<(unsigned)grid, WARPS * 32, 0, s>>>(va);
+static void launch_var(int kid, const VarArgs& va, long long nwin, cudaStream_t s) {
+  switch (kid) {
+    case KID_RBF: launch_var_k<NT_MAX, WARPS, KID_RBF>(va, nwin, s); break;
+    case KID_RBF_PER: launch_var_k<NT_MAX, WARPS, KID_RBF_PER>(va, nwin, s); break;
+    case KID_RBF_BROWN: launch_var_k<NT_MAX, WARPS, KID_RBF_BROWN>(va, nwin, s); break;
+    default: launch_var_k<NT_MAX, WARPS, KID_GENERIC>(va, nwin, s); break;
+  }
+}
+static void launch_fit(int kid, const FitArgs& fa, long long nprob, cudaStream_t s) {
+  switch (kid) {
+    case KID_RBF: gp_fit_kernel<KID_RBF><<<(unsigned)nprob, FIT_THREADS, 0, s>>>(fa); break;
+    case KID_RBF_PER: gp_fit_kernel<KID_RBF_PER><<<(unsigned)nprob, FIT_THREADS, 0, s>>>(fa); break;
+    case KID_RBF_BROWN: gp_fit_kernel<KID_RBF_BROWN><<<(unsigned)nprob, FIT_THREADS, 0, s>>>(fa); break;
+    default: gp_fit_kernel<KID_GENERIC><<<(unsigned)nprob, FIT_THREADS, 0, s>>>(fa); break;
+  }
 }
 
 extern "C" int cngp_predict_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t theta_stride,
@@ -363,31 +441,37 @@ extern "C" int cngp_predict_batch(cngp_ctx* ctx, const cngp_kernel* kernel, cons
   }
 
   const int nt = (N + 7) / 8, mt = (M + 7) / 8;
-  const size_t per_problem = ((size_t)tiles_in_lower(nt) * 64 + (size_t)nt * 8) * sizeof(double);
-  const long long chunk = std::max<long long>(1, (long long)(ctx->scratch_bytes / per_problem));
+  const int kid = match_fast_kernel(kp);
+  const size_t per_problem = ((size_t)tiles_in_lower(nt) * 64 + (size_t)nt * 8 * 5) * sizeof(double);
+  const size_t slack = VAR_CHUNK_DOUBLES;   // gp_var_kernel's first (partial) chunk may start before the first tile
+  const long long chunk = std::max<long long>(1, (long long)((ctx->scratch_bytes - slack * 8) / per_problem));
   for (long long w0 = 0; w0 < B; w0 += chunk) {
     const long long nw = std::min<long long>(chunk, B - w0);
-    double* Lbuf = ctx->scratch;
-    double* zbuf = ctx->scratch + (size_t)nw * tiles_in_lower(nt) * 64;
+    double* Lbuf = ctx->scratch + slack;
+    double* zbuf = Lbuf + (size_t)nw * tiles_in_lower(nt) * 64;
+    double* fbuf = zbuf + (size_t)nw * nt * 8;
     FitArgs fa;
     fa.kp = kp;
     fa.theta = d_theta; fa.theta_stride = theta_stride; fa.theta_mode = theta_stride ? 1 : 0;
     fa.x = d_x; fa.y = d_y; fa.N = N; fa.nt = nt; fa.n_windows = (int)B; fa.problem0 = w0;
-    fa.L = Lbuf; fa.z = zbuf; fa.lml = d_lml; fa.logdet = nullptr; fa.quad = nullptr; fa.status = d_status;
+    fa.L = Lbuf; fa.z = zbuf; fa.feat = fbuf; fa.lml = d_lml; fa.logdet = nullptr; fa.quad = nullptr;
+    fa.status = d_status;
     fa.jitter_retry = ctx->cfg.jitter_retry;
-    gp_fit_kernel<<<(unsigned)nw, FIT_THREADS, 0, ctx->stream>>>(fa);
-    ctx->launches++;
+    ctx->begin(CNGP_PROF_FIT);
+    launch_fit(kid, fa, nw, ctx->stream);
+    ctx->end();
     if (M > 0) {
       VarArgs va;
       va.kp = kp;
       va.theta = d_theta; va.theta_stride = theta_stride; va.theta_mode = theta_stride ? 1 : 0;
-      va.x = d_x; va.xstar = d_xs; va.xstar_stride = xstar_stride;
+      va.xstar = d_xs; va.xstar_stride = xstar_stride;
       va.N = N; va.nt = nt; va.M = M; va.mt = mt; va.window0 = w0; va.n_windows_launch = nw;
-      va.L = Lbuf; va.z = zbuf; va.status = d_status; va.mean = d_mean; va.var = d_var;
-      if (nt <= 8) launch_var<8, 8>(va, nw, ctx->stream);
-      else if (nt <= 16) launch_var<16, 8>(va, nw, ctx->stream);
-      else launch_var<32, 12>(va, nw, ctx->stream);
-      ctx->launches++;
+      va.L = Lbuf; va.z = zbuf; va.feat = fbuf; va.status = d_status; va.mean = d_mean; va.var = d_var;
+      ctx->begin(CNGP_PROF_VAR);
+      if (nt <= 8) launch_var<8, 16>(kid, va, nw, ctx->stream);
+      else if (nt <= 16) launch_var<16, 16>(kid, va, nw, ctx->stream);
+      else launch_var<32, 12>(kid, va, nw, ctx->stream);
+      ctx->end();
     }
     CU(ctx, cudaGetLastError());
   }
@@ -441,18 +525,21 @@ extern "C" int cngp_lml_grad_batch(cngp_ctx* ctx, const cngp_kernel* kernel, con
     fa.kp = kp;
     fa.theta = d_theta; fa.theta_stride = P; fa.theta_mode = 2;
     fa.x = d_x; fa.y = d_y; fa.N = N; fa.nt = nt; fa.n_windows = (int)B; fa.problem0 = p0;
-    fa.L = Lbuf; fa.z = zbuf; fa.lml = d_lml; fa.logdet = nullptr; fa.quad = nullptr; fa.status = d_status;
+    fa.L = Lbuf; fa.z = zbuf; fa.feat = nullptr; fa.lml = d_lml; fa.logdet = nullptr; fa.quad = nullptr;
+    fa.status = d_status;
     fa.jitter_retry = ctx->cfg.jitter_retry;
-    gp_fit_kernel<<<(unsigned)np, FIT_THREADS, 0, ctx->stream>>>(fa);
-    ctx->launches++;
+    ctx->begin(CNGP_PROF_FIT);
+    launch_fit(match_fast_kernel(kp), fa, np, ctx->stream);
+    ctx->end();
     if (grad) {
       GradArgs ga;
       ga.kp = kp;
       ga.theta = d_theta; ga.theta_stride = P;
       ga.x = d_x; ga.N = N; ga.nt = nt; ga.n_windows = (int)B; ga.problem0 = p0;
       ga.L = Lbuf; ga.W = Wbuf; ga.z = zbuf; ga.alpha = abuf; ga.status = d_status; ga.grad = d_grad;
+      ctx->begin(CNGP_PROF_GRAD);
       gp_grad_kernel<<<(unsigned)np, GRAD_THREADS, 0, ctx->stream>>>(ga);
-      ctx->launches++;
+      ctx->end();
     }
     CU(ctx, cudaGetLastError());
   }
@@ -501,9 +588,10 @@ extern "C" int cngp_zupt_lookahead_batch(cngp_ctx* ctx, const double* mean, cons
   if (!d_step) d_step = (int*)ctx->buf(14, sizeof(int) * (size_t)B);
   if (!d_xy) d_xy = (double*)ctx->buf(13, sizeof(double) * (size_t)B);
   if (!d_step || !d_xy) return fail(ctx, CNGP_ERR_NOMEM, "lookahead: buffers");
+  ctx->begin(CNGP_PROF_LOOKAHEAD);
   const int e = cngp_launch_lookahead(d_mean, d_sigma, B, M, d_P, d_Q, d_F, d_H, d_pos, per_window, &c, d_trig, d_i,
                                       d_step, d_xy, ctx->stream);
-  ctx->launches++;
+  ctx->end();
   if (e) return fail(ctx, CNGP_ERR_CUDA, "lookahead launch: %s", cudaGetErrorString((cudaError_t)e));
   const int rc = st.finish();
   if (rc) return fail(ctx, rc, "lookahead: copy-out failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -522,8 +610,9 @@ extern "C" int cngp_llh_to_enu(cngp_ctx* ctx, const double* llh, int64_t n, cons
   const double* d_in = (const double*)st.in(llh, sizeof(double) * 3 * (size_t)n);
   double* d_out = (double*)st.out(enu, sizeof(double) * 3 * (size_t)n);
   if (st.err) return fail(ctx, st.err, "llh_to_enu: staging failed");
+  ctx->begin(CNGP_PROF_MISC);
   const int e = cngp_launch_llh_to_enu(d_in, n, &c, d_out, ctx->stream);
-  ctx->launches++;
+  ctx->end();
   if (e) return fail(ctx, CNGP_ERR_CUDA, "llh_to_enu launch: %s", cudaGetErrorString((cudaError_t)e));
   const int rc = st.finish();
   if (rc) return fail(ctx, rc, "llh_to_enu: copy-out failed");

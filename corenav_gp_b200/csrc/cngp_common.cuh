@@ -45,13 +45,40 @@ __device__ __forceinline__ void tile_store(double* tile, int lane, const tile2& 
   *reinterpret_cast<double2*>(tile + 2 * lane) = make_double2(t.a, t.b);
 }
 
-// Column-block-major packed lower-triangular tile storage, indexed from the LAST tile column so that offsets do not
-// depend on the number of tile rows nt:  column j (J = nt-1-j) starts at J(J+1)/2 tiles and holds tiles i = j..nt-1.
+// Packed lower-triangular tile storage, column-major: column j holds tiles i = j..nt-1 and starts after the
+// nt + (nt-1) + ... tiles of columns 0..j-1.  Seen from the END of the buffer, column j (J = nt-1-j) starts
+// (J+1)(J+2)/2 tiles before the end - independent of nt - and the forward substitution of gp_var.cuh consumes the
+// tiles in exactly this linear order, which is what lets it stream them with bulk asynchronous copies.
 __host__ __device__ __forceinline__ int tile_index(int i, int j, int nt) {
-  const int J = nt - 1 - j;
-  return J * (J + 1) / 2 + (i - j);
+  return j * nt - j * (j - 1) / 2 + (i - j);
 }
 __host__ __device__ __forceinline__ int tiles_in_lower(int nt) { return nt * (nt + 1) / 2; }
+
+// ---- mbarrier + bulk asynchronous copy (TMA, 1-D) helpers ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared bulk copy, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src_gmem), "r"(bytes), "r"(bar)
+               : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // covariance functions.  A kernel expression (postfix program, cngp.h) is expanded on the host into a sum of

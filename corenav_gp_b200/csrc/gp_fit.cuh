@@ -17,6 +17,7 @@ namespace cngp {
 constexpr int FIT_WARPS = 8;
 constexpr int FIT_THREADS = FIT_WARPS * 32;
 constexpr int FIT_MAXT = 5;  // ceil((32 + 1) / 8) row tiles per warp in the first column
+constexpr int NPAD = CNGP_MAX_N + 8;
 
 struct FitArgs {
   KProg kp;
@@ -30,6 +31,7 @@ struct FitArgs {
   long long problem0;    // first problem of this launch (chunking)
   double* L;             // [chunk][tiles_in_lower(nt)][64]
   double* z;             // [chunk][nt*8]   z = L^-1 y
+  double* feat;          // [chunk][4][nt*8] per-point features (x, x^2, cos, sin) for phase B, or null
   double* lml;           // [n_problems] or null
   double* logdet;        // [n_problems] or null
   double* quad;          // [n_problems] or null   y' Ky^-1 y
@@ -85,11 +87,13 @@ __device__ __forceinline__ int chol8_inv8(tile2 c, int lane, double* dt, double*
   return fail;
 }
 
+template <int KID>
 __global__ void __launch_bounds__(FIT_THREADS) gp_fit_kernel(const FitArgs a) {
-  __shared__ double xs[CNGP_MAX_N + 8];
-  __shared__ double ys[CNGP_MAX_N + 8];
-  __shared__ double zs[CNGP_MAX_N + 8];
+  __shared__ double fx[NPAD], fxx[NPAD], fc[NPAD], fs[NPAD];   // per-point features
+  __shared__ double ys[NPAD];
+  __shared__ double zs[NPAD];
   __shared__ LeafConst hc[CNGP_MAX_LEAVES];
+  __shared__ KProg kps;
   __shared__ __align__(16) double dt[64];
   __shared__ __align__(16) double linv[64];
   __shared__ double rsd[8];
@@ -106,86 +110,120 @@ __global__ void __launch_bounds__(FIT_THREADS) gp_fit_kernel(const FitArgs a) {
   const double* th = a.theta + ti * a.theta_stride;
   const int N = a.N, nt = a.nt;
   const double noise = th[a.kp.n_params];
+  FastK<KID> fk;
+  if (KID != KID_GENERIC) fk.init(th);
 
   for (int i = tid; i < nt * 8; i += FIT_THREADS) {
-    xs[i] = i < N ? a.x[(long long)win * N + i] : 0.0;
+    const double xv = i < N ? a.x[(long long)win * N + i] : 0.0;
     ys[i] = i < N ? a.y[(long long)win * N + i] : 0.0;
+    PointFeat f{xv, __dmul_rn(xv, xv), 0.0, 0.0};
+    if (KID != KID_GENERIC) f = fk.point(xv);
+    fx[i] = f.x; fxx[i] = f.xx; fc[i] = f.c; fs[i] = f.s;
+    if (a.feat) {
+      double* fp = a.feat + lp * (long long)(4 * nt * 8);
+      fp[i] = f.x; fp[nt * 8 + i] = f.xx; fp[2 * nt * 8 + i] = f.c; fp[3 * nt * 8 + i] = f.s;
+    }
   }
-  if (tid < a.kp.n_leaves) hc[tid] = leaf_prepare(a.kp.leaf_type[tid], th + a.kp.leaf_param[tid]);
+  if (KID == KID_GENERIC) {
+    if (tid < a.kp.n_leaves) hc[tid] = leaf_prepare(a.kp.leaf_type[tid], th + a.kp.leaf_param[tid]);
+    if (tid == 0) kps = a.kp;
+  }
   __syncthreads();
+
+  // Ky(row, col) from the staged features; identity padding beyond N
+  auto ky_entry = [&](int row, int col, const PointFeat& fa, const PointFeat& fb) -> double {
+    if (row < N && col < N) {
+      if (KID == KID_GENERIC) return keval_generic_sym(&kps, hc, fa.x, fb.x, row == col);
+      return fk.eval(fa, fb, row == col);
+    }
+    return (row == col) ? 1.0 : 0.0;
+  };
+  auto feat_at = [&](int i) -> PointFeat {
+    if (KID == KID_GENERIC) return PointFeat{fx[i], 0.0, 0.0, 0.0};
+    if (KID == KID_RBF_PER) return PointFeat{fx[i], fxx[i], fc[i], fs[i]};
+    return PointFeat{fx[i], fxx[i], 0.0, 0.0};
+  };
 
   double* Lp = a.L + lp * (long long)tiles_in_lower(nt) * 64;
   const int max_attempts = a.jitter_retry ? 6 : 1;
-  double extra = 0.0, jit_base = 0.0;
+  double extra = 0.0;
   int fail_pivot = 0, attempts_used = 0;
 
   for (int attempt = 0; attempt < max_attempts; ++attempt) {
     if (attempt == 1) {
       // GPy jitchol: jitter = mean(diag(Ky)) * 1e-6, then x10 per retry
       double s = 0.0;
-      for (int i = tid; i < N; i += FIT_THREADS) s += keval<true>(a.kp, hc, xs[i], xs[i], true) + noise + CNGP_JITTER;
+      for (int i = tid; i < N; i += FIT_THREADS) {
+        const PointFeat f = feat_at(i);
+        s += ky_entry(i, i, f, f) + noise + CNGP_JITTER;
+      }
       for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) s_red[w] = s;
       __syncthreads();
       s = 0.0;
       for (int i = 0; i < FIT_WARPS; ++i) s += s_red[i];
-      jit_base = s / N * 1e-6;
-      extra = jit_base;
+      extra = s / N * 1e-6;
     } else if (attempt > 1) {
       extra *= 10.0;
     }
     if (tid == 0) { s_fail = 0; s_hl = 0.0; }
     __syncthreads();
+    const double dadd = noise + CNGP_JITTER + extra;
 
     for (int j = 0; j < nt; ++j) {
-      // ---- left-looking update of tile column j: S_t = sum_{k<j} L(i_t,k) L(j,k)^T ----
+      // my row tiles of this column: i_t = j + w + 8 t  (t < nvalid), plus possibly the z row (i == nt)
+      const int rem = nt - j - w;                       // i_t < nt  <=>  8 t < rem
+      const int nvalid = rem > 0 ? min(FIT_MAXT, (rem + 7) >> 3) : 0;
+      const bool zmine = rem >= 0 && (rem & 7) == 0 && (rem >> 3) < FIT_MAXT;
+      // ---- left-looking update: S_t = sum_{k<j} L(i_t,k) L(j,k)^T;  column k starts at cb, tile (i,k) at cb+(i-k)*64
       tile2 S[FIT_MAXT];
 #pragma unroll
       for (int t = 0; t < FIT_MAXT; ++t) S[t] = tile2{0.0, 0.0};
+      tile2 Sz{0.0, 0.0};
+      const double* cb = Lp + 2 * lane;
+#pragma unroll 2
       for (int k = 0; k < j; ++k) {
-        const tile2 Y = tile_load(Lp + (long long)tile_index(j, k, nt) * 64, lane);
+        const double* py = cb + (j - k) * 64;
+        const double* px = py + w * 64;
+        const double2 yv = *reinterpret_cast<const double2*>(py);
+        const tile2 Y{yv.x, yv.y};
 #pragma unroll
         for (int t = 0; t < FIT_MAXT; ++t) {
-          const int i = j + w + FIT_WARPS * t;
-          if (i < nt) {
-            const tile2 X = tile_load(Lp + (long long)tile_index(i, k, nt) * 64, lane);
-            tile_mma(S[t], X, Y);
-          } else if (i == nt) {
-            tile2 X{0.0, 0.0};
-            if (r == 0) { X.a = zs[8 * k + 2 * q]; X.b = zs[8 * k + 2 * q + 1]; }
-            tile_mma(S[t], X, Y);
+          if (t < nvalid) {
+            const double2 xv = *reinterpret_cast<const double2*>(px + t * (FIT_WARPS * 64));
+            tile_mma(S[t], tile2{xv.x, xv.y}, Y);
           }
         }
+        if (zmine) {
+          tile2 X{0.0, 0.0};
+          if (r == 0) { X.a = zs[8 * k + 2 * q]; X.b = zs[8 * k + 2 * q + 1]; }
+          tile_mma(Sz, X, Y);
+        }
+        cb += (nt - k) * 64;
       }
       // ---- C_t = Ky tile - S_t (Ky evaluated here, never stored) ----
+      {
+        const int c0 = 8 * j + 2 * q, c1 = c0 + 1;
+        const PointFeat fc0 = feat_at(c0), fc1 = feat_at(c1);
 #pragma unroll
-      for (int t = 0; t < FIT_MAXT; ++t) {
-        const int i = j + w + FIT_WARPS * t;
-        if (i < nt) {
-          const int row = 8 * i + r, c0 = 8 * j + 2 * q, c1 = c0 + 1;
-          double v0, v1;
-          if (row < N && c0 < N) {
-            v0 = keval<true>(a.kp, hc, xs[row], xs[c0], row == c0);
-            if (row == c0) v0 += noise + CNGP_JITTER + extra;
-          } else {
-            v0 = (row == c0) ? 1.0 : 0.0;
+        for (int t = 0; t < FIT_MAXT; ++t) {
+          if (t < nvalid) {
+            const int row = 8 * (j + w + FIT_WARPS * t) + r;
+            const PointFeat fr = feat_at(row);
+            double v0 = ky_entry(row, c0, fr, fc0), v1 = ky_entry(row, c1, fr, fc1);
+            if (row == c0 && row < N) v0 += dadd;
+            if (row == c1 && row < N) v1 += dadd;
+            S[t].a = v0 - S[t].a;
+            S[t].b = v1 - S[t].b;
           }
-          if (row < N && c1 < N) {
-            v1 = keval<true>(a.kp, hc, xs[row], xs[c1], row == c1);
-            if (row == c1) v1 += noise + CNGP_JITTER + extra;
-          } else {
-            v1 = (row == c1) ? 1.0 : 0.0;
-          }
-          S[t].a = v0 - S[t].a;
-          S[t].b = v1 - S[t].b;
-        } else if (i == nt) {
-          const double v0 = (r == 0) ? ys[8 * j + 2 * q] : 0.0;
-          const double v1 = (r == 0) ? ys[8 * j + 2 * q + 1] : 0.0;
-          S[t].a = v0 - S[t].a;
-          S[t].b = v1 - S[t].b;
+        }
+        if (zmine) {
+          Sz.a = ((r == 0) ? ys[c0] : 0.0) - Sz.a;
+          Sz.b = ((r == 0) ? ys[c1] : 0.0) - Sz.b;
         }
       }
       // ---- diagonal tile: factor + invert (warp 0 owns i == j at t == 0) ----
+      double* colj = Lp + (long long)tile_index(j, j, nt) * 64;
       if (w == 0) {
         double hl = 0.0;
         const int f = chol8_inv8(S[0], lane, dt, linv, rsd, &hl);
@@ -193,24 +231,23 @@ __global__ void __launch_bounds__(FIT_THREADS) gp_fit_kernel(const FitArgs a) {
           if (f && s_fail == 0) s_fail = 8 * j + f;
           s_hl += hl;
         }
-        tile_store(Lp + (long long)tile_index(j, j, nt) * 64, lane, tile_load(linv, lane));
+        tile_store(colj, lane, tile_load(linv, lane));
       }
       __syncthreads();
       // ---- rows below: L(i,j) = C_t inv(L_jj)^T ----
       const tile2 Yinv = tile_load(linv, lane);
 #pragma unroll
       for (int t = 0; t < FIT_MAXT; ++t) {
-        const int i = j + w + FIT_WARPS * t;
-        if (i > j && i <= nt) {
+        if (t < nvalid && (w + t) > 0) {
           tile2 Lt{0.0, 0.0};
           tile_mma(Lt, S[t], Yinv);
-          if (i < nt) {
-            tile_store(Lp + (long long)tile_index(i, j, nt) * 64, lane, Lt);
-          } else if (r == 0) {
-            zs[8 * j + 2 * q] = Lt.a;
-            zs[8 * j + 2 * q + 1] = Lt.b;
-          }
+          tile_store(colj + (w + FIT_WARPS * t) * 64, lane, Lt);
         }
+      }
+      if (zmine) {
+        tile2 Lt{0.0, 0.0};
+        tile_mma(Lt, Sz, Yinv);
+        if (r == 0) { zs[8 * j + 2 * q] = Lt.a; zs[8 * j + 2 * q + 1] = Lt.b; }
       }
       __syncthreads();
     }

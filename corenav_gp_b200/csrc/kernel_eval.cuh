@@ -168,4 +168,110 @@ __host__ __device__ __forceinline__ int leaf_nparams(int type) {
   return (type == CNGP_K_RATQUAD || type == CNGP_K_STDPERIODIC) ? 3 : (type >= CNGP_K_BROWNIAN ? 1 : 2);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Specialised evaluators.  The composite kernels the reference actually deploys or benchmarks get a straight-line
+// evaluator built from per-point features computed once per point (x, x^2 and, for the periodic leaf, cos/sin of the
+// phase 2 pi x / p so that  sin^2(pi (x-x')/p) = (1 - cos(phi - phi'))/2  needs two fma instead of a sin), and an
+// exp that is 16 FP64 operations (Cody-Waite reduction + degree-12 polynomial, ~1 ulp) - the kernel matrix is
+// (N^2/2 + N M) evaluations per window, the same order of work as the factorisation.
+//   KID 0  generic sum-of-products interpreter (any expression)
+//   KID 1  rbf                       (BASELINE.json configs[0])
+//   KID 2  rbf + stdperiodic         (configs[1..2], "SE + periodic")
+//   KID 3  rbf * brownian            (the deployed kernel, gp_slip_node.py:31)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int KID_GENERIC = 0, KID_RBF = 1, KID_RBF_PER = 2, KID_RBF_BROWN = 3;
+
+// exp(x) for x <= ~1 (kernel exponents are never positive); flushes to 0 below -708.
+__device__ __forceinline__ double fast_exp(double x) {
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest integer in the low word
+  const double t = fma(x, 1.4426950408889634, magic);
+  const int n = __double2loint(t);
+  const double nd = t - magic;
+  double f = fma(nd, -6.93147180369123816490e-01, x);
+  f = fma(nd, -1.90821492927058770002e-10, f);
+  double p = 2.08767569878680989792e-09;           // 1/12!
+  p = fma(p, f, 2.50521083854417187751e-08);       // 1/11!
+  p = fma(p, f, 2.75573192239858906526e-07);       // 1/10!
+  p = fma(p, f, 2.75573192239858906526e-06);       // 1/9!
+  p = fma(p, f, 2.48015873015873015873e-05);       // 1/8!
+  p = fma(p, f, 1.98412698412698412698e-04);       // 1/7!
+  p = fma(p, f, 1.38888888888888888889e-03);       // 1/6!
+  p = fma(p, f, 8.33333333333333333333e-03);       // 1/5!
+  p = fma(p, f, 4.16666666666666666667e-02);       // 1/4!
+  p = fma(p, f, 1.66666666666666666667e-01);       // 1/3!
+  p = fma(p, f, 0.5);
+  p = fma(p, f, 1.0);
+  p = fma(p, f, 1.0);
+  const double r = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+  return x < -708.0 ? 0.0 : r;
+}
+
+struct PointFeat {
+  double x, xx, c, s;  // x, x*x, cos(2 pi x / p), sin(2 pi x / p)
+};
+
+template <int KID>
+struct FastK {
+  double c0, c1, c2, c3, c4;
+  __device__ __forceinline__ void init(const double* th) {
+    c0 = th[0];
+    c1 = -0.5 / (th[1] * th[1]);
+    if (KID == KID_RBF_PER) {
+      c2 = 2.0 * 3.14159265358979323846 / th[3];   // phase scale 2 pi / period
+      c3 = 0.25 / (th[4] * th[4]);                 // A = 1 / (4 l^2): -0.5 sin^2 / l^2 = A (cos(dphi) - 1)
+      c4 = th[2];
+    } else if (KID == KID_RBF_BROWN) {
+      c4 = th[2];
+    }
+  }
+  __device__ __forceinline__ PointFeat point(double x) const {
+    PointFeat f{x, __dmul_rn(x, x), 0.0, 0.0};
+    if (KID == KID_RBF_PER) sincos(x * c2, &f.s, &f.c);
+    return f;
+  }
+  // GPy expanded-form r^2 from the features (same roundings as r2_expanded; -2 m is exact so the fma is too)
+  __device__ __forceinline__ double r2(const PointFeat& a, const PointFeat& b) const {
+    return fma(-2.0, __dmul_rn(a.x, b.x), __dadd_rn(a.xx, b.xx));
+  }
+  __device__ __forceinline__ double eval(const PointFeat& a, const PointFeat& b, bool same_sym) const {
+    double rr = r2(a, b);
+    if (same_sym) rr = 0.0;
+    const double e1 = c0 * fast_exp(fmin(rr * c1, 0.0));   // fmin == GPy's clip of r2 at 0
+    if (KID == KID_RBF) return e1;
+    if (KID == KID_RBF_PER) {
+      const double cd = fma(a.c, b.c, a.s * b.s);          // cos(phi_a - phi_b)
+      return fma(c4, fast_exp(fmin(fma(c3, cd, -c3), 0.0)), e1);
+    }
+    // rbf * brownian
+    const bool agree = (a.x > 0.0 && b.x > 0.0) || (a.x < 0.0 && b.x < 0.0) || (a.x == 0.0 && b.x == 0.0);
+    return agree ? e1 * (c4 * fmin(fabs(a.x), fabs(b.x))) : 0.0;
+  }
+  __device__ __forceinline__ double kdiag(double x) const {
+    if (KID == KID_RBF) return c0;
+    if (KID == KID_RBF_PER) return c0 + c4;
+    return c0 * (c4 * fabs(x));
+  }
+};
+
+// Uniform front end used by the kernels: KID 0 forwards to the interpreter (kept out of line so the unrolled
+// callers stay small), KID > 0 to FastK.
+__device__ __noinline__ double keval_generic_sym(const KProg* kp, const LeafConst* hc, double xa, double xb, bool same) {
+  return keval<true>(*kp, hc, xa, xb, same);
+}
+__device__ __noinline__ double keval_generic_cross(const KProg* kp, const LeafConst* hc, double xa, double xb) {
+  return keval<false>(*kp, hc, xa, xb, false);
+}
+
+// which specialised evaluator (if any) matches a sum-of-products program
+__host__ inline int match_fast_kernel(const KProg& kp) {
+  if (kp.n_terms == 1 && kp.n_leaves == 1 && kp.leaf_type[0] == CNGP_K_RBF) return KID_RBF;
+  if (kp.n_terms == 2 && kp.n_leaves == 2 && kp.leaf_type[0] == CNGP_K_RBF && kp.leaf_type[1] == CNGP_K_STDPERIODIC &&
+      kp.leaf_param[0] == 0 && kp.leaf_param[1] == 2)
+    return KID_RBF_PER;
+  if (kp.n_terms == 1 && kp.n_leaves == 2 && kp.leaf_type[0] == CNGP_K_RBF && kp.leaf_type[1] == CNGP_K_BROWNIAN &&
+      kp.leaf_param[0] == 0 && kp.leaf_param[1] == 2)
+    return KID_RBF_BROWN;
+  return KID_GENERIC;
+}
+
 }  // namespace cngp

@@ -91,11 +91,25 @@ int cngp_create(const cngp_config* cfg, cngp_ctx** out);
 void cngp_destroy(cngp_ctx* ctx);
 const char* cngp_last_error(cngp_ctx* ctx); /* ctx may be NULL: last create error */
 int cngp_sync(cngp_ctx* ctx);
-/* Make the context launch on an existing cudaStream_t (e.g. torch's current stream); NULL = the context's own. */
-int cngp_set_stream(cngp_ctx* ctx, void* cuda_stream);
+/* Make the context launch on an existing cudaStream_t (e.g. torch's current stream; 0 is the legacy default
+ * stream), or back on the context's own non-blocking stream when use_own != 0. */
+int cngp_set_stream(cngp_ctx* ctx, void* cuda_stream, int32_t use_own);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t cngp_launch_count(cngp_ctx* ctx);
 int cngp_version(void);
+
+/* Per-kernel device timing with CUDA events recorded on the launching stream around every kernel this context
+ * launches (bench.py's roofline numbers).  cngp_profile_read synchronises the recorded events, returns the accumulated
+ * milliseconds and launch count of one kernel class, and optionally resets them. */
+#define CNGP_PROF_FIT 0        /* gp_fit_kernel: assembly + Cholesky + z + LML */
+#define CNGP_PROF_VAR 1        /* gp_var_kernel: predictive mean / variance */
+#define CNGP_PROF_GRAD 2       /* gp_grad_kernel: L^-1, K^-1, gradient contraction */
+#define CNGP_PROF_LOOKAHEAD 3  /* zupt_lookahead_kernel */
+#define CNGP_PROF_LARGE 4      /* large-N blocked Cholesky kernels */
+#define CNGP_PROF_MISC 5
+#define CNGP_PROF_KERNELS 6
+int cngp_set_profiling(cngp_ctx* ctx, int32_t on);
+int cngp_profile_read(cngp_ctx* ctx, int32_t kernel_id, double* total_ms, int64_t* launches, int32_t reset);
 
 /* Exact-GP prediction for B independent windows (rows a3 + a6).
  *   theta   [B][P] (theta_stride = P) or one shared vector (theta_stride = 0); P = kernel->n_params + 1, noise last
