@@ -383,12 +383,10 @@ template <int NT_MAX, int WARPS, int KID>
 static void launch_var_k(const VarArgs& va, long long nwin, cudaStream_t s) {
   const long long grid = std::min<long long>(nwin, g_sm_count);   // persistent: one CTA per SM
   const size_t smem = var_smem_bytes(WARPS);
-  static bool attr_done = false;   // one process per GPU: per-instantiation, set once
-  if (!attr_done) {
-    cudaFuncSetAttribute(gp_var_kernel<NT_MAX, WARPS, KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
-  gp_var_kernel<NT_MAX, WARPS, KID><<<(unsigned)grid, WARPS * 32, smem, s>>>(va);
+  const bool full = va.nt == NT_MAX && va.N == NT_MAX * 8;
+  auto kfn = full ? gp_var_kernel<NT_MAX, WARPS, KID, true> : gp_var_kernel<NT_MAX, WARPS, KID, false>;
+  cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kfn<<<(unsigned)grid, WARPS * 32, smem, s>>>(va);
 }
 template <int NT_MAX, int WARPS>
 static void launch_var(int kid, const VarArgs& va, long long nwin, cudaStream_t s) {
@@ -399,12 +397,24 @@ static void launch_var(int kid, const VarArgs& va, long long nwin, cudaStream_t 
     default: launch_var_k<NT_MAX, WARPS, KID_GENERIC>(va, nwin, s); break;
   }
 }
+template <int KID, int WARPS>
+static void launch_fit_k(const FitArgs& fa, long long nprob, cudaStream_t s) {
+  const size_t smem = fit_smem_bytes(fa.nt);
+  cudaFuncSetAttribute(gp_fit_kernel<KID, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  gp_fit_kernel<KID, WARPS><<<(unsigned)nprob, WARPS * 32, smem, s>>>(fa);
+}
+template <int KID>
+static void launch_fit_w(const FitArgs& fa, long long nprob, cudaStream_t s) {
+  // row tiles per column <= nt + 1 must fit WARPS * FIT_MAXT
+  if (fa.nt + 1 <= 8 * FIT_MAXT) launch_fit_k<KID, 8>(fa, nprob, s);
+  else launch_fit_k<KID, 16>(fa, nprob, s);
+}
 static void launch_fit(int kid, const FitArgs& fa, long long nprob, cudaStream_t s) {
   switch (kid) {
-    case KID_RBF: gp_fit_kernel<KID_RBF><<<(unsigned)nprob, FIT_THREADS, 0, s>>>(fa); break;
-    case KID_RBF_PER: gp_fit_kernel<KID_RBF_PER><<<(unsigned)nprob, FIT_THREADS, 0, s>>>(fa); break;
-    case KID_RBF_BROWN: gp_fit_kernel<KID_RBF_BROWN><<<(unsigned)nprob, FIT_THREADS, 0, s>>>(fa); break;
-    default: gp_fit_kernel<KID_GENERIC><<<(unsigned)nprob, FIT_THREADS, 0, s>>>(fa); break;
+    case KID_RBF: launch_fit_w<KID_RBF>(fa, nprob, s); break;
+    case KID_RBF_PER: launch_fit_w<KID_RBF_PER>(fa, nprob, s); break;
+    case KID_RBF_BROWN: launch_fit_w<KID_RBF_BROWN>(fa, nprob, s); break;
+    default: launch_fit_w<KID_GENERIC>(fa, nprob, s); break;
   }
 }
 

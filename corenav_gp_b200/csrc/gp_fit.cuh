@@ -14,10 +14,19 @@
 
 namespace cngp {
 
-constexpr int FIT_WARPS = 8;
-constexpr int FIT_THREADS = FIT_WARPS * 32;
-constexpr int FIT_MAXT = 5;  // ceil((32 + 1) / 8) row tiles per warp in the first column
+constexpr int FIT_MAXT = 3;  // row tiles per warp in the first column: ceil((nt + 1) / warps) <= 3
 constexpr int NPAD = CNGP_MAX_N + 8;
+// Shared-memory tile pool.  With h = ceil(nt/2): region A holds the packed lower triangle of the top-left h x h tile
+// block while columns k < h are being factored, region B the (nt-h) x h block below it; rows < h are dead once column
+// h starts, so columns k >= h (the packed lower triangle of the trailing (nt-h) x (nt-h) block) reuse region A.
+// 392 tiles (196 KB) at nt = 32 instead of 528.
+__host__ __device__ __forceinline__ int fit_pool_tiles(int nt) {
+  const int h = (nt + 1) / 2;
+  return h * (h + 1) / 2 + (nt - h) * h;
+}
+constexpr size_t fit_smem_bytes(int nt) {
+  return (size_t)(((nt + 1) / 2) * ((nt + 1) / 2 + 1) / 2 + (nt - (nt + 1) / 2) * ((nt + 1) / 2)) * 512;
+}
 
 struct FitArgs {
   KProg kp;
@@ -39,34 +48,39 @@ struct FitArgs {
   int jitter_retry;
 };
 
-// In-warp Cholesky of an 8x8 SPD tile held in the lane layout, followed by the inverse of the factor.
-// dt / linv: 64-double shared scratch private to the calling warp.  Returns the failing pivot (1-based) or 0;
-// adds sum(log L_kk) to *half_logdet.  On return linv holds inv(L) row-major (zeros above the diagonal).
-__device__ __forceinline__ int chol8_inv8(tile2 c, int lane, double* dt, double* linv, double* rsd, double* half_logdet) {
+// In-warp Cholesky of an 8x8 SPD tile held in the lane layout, followed by the inverse of the factor.  This sits on
+// the critical path of every tile column, so it is built for latency: the tile stays in registers, column k is
+// exchanged with four shuffles per step, the pivot uses rsqrt (sqrt + div cost 165 dependent cycles, rsqrt 80), and
+// the logarithms of the pivots are NOT taken here - the pivots are parked in dpiv and logged in parallel at the end.
+// dt / linv: 64-double shared scratch private to the calling warp.  Returns the failing pivot (1-based) or 0.
+// On return linv holds inv(L) row-major (zeros above the diagonal) and dpiv[0..7] the diagonal of L.
+__device__ __forceinline__ int chol8_inv8(tile2 c, int lane, double* dt, double* linv, double* dpiv) {
   const int r = lane >> 2, q = lane & 3;
-  tile_store(dt, lane, c);
-  __syncwarp();
   int fail = 0;
-  double hl = 0.0;
+  double rsv[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const double pk = dt[k * 8 + k];
+    const double v = (k & 1) ? c.b : c.a;                              // my entry of column pair k>>1
+    const double pk = __shfl_sync(0xffffffffu, v, 4 * k + (k >> 1));     // T[k][k]
+    const double trk = __shfl_sync(0xffffffffu, v, 4 * r + (k >> 1));    // T[r][k]
+    const double tc0 = __shfl_sync(0xffffffffu, v, 8 * q + (k >> 1));    // T[2q][k]
+    const double tc1 = __shfl_sync(0xffffffffu, v, 8 * q + 4 + (k >> 1));// T[2q+1][k]
     if (!(pk > 0.0) && fail == 0) fail = k + 1;
-    const double d = sqrt(pk);
-    const double rs = 1.0 / d;
-    hl += log(d);
-    const double lrk = dt[r * 8 + k] * rs;
-    const double lc0 = dt[(2 * q) * 8 + k] * rs;
-    const double lc1 = dt[(2 * q + 1) * 8 + k] * rs;
-    __syncwarp();
-    if (2 * q > k && r >= 2 * q) { c.a -= lrk * lc0; dt[r * 8 + 2 * q] = c.a; }
-    if (2 * q + 1 > k && r >= 2 * q + 1) { c.b -= lrk * lc1; dt[r * 8 + 2 * q + 1] = c.b; }
-    if (2 * q == k && r >= k) { c.a = (r == k) ? d : lrk; dt[r * 8 + k] = c.a; }
-    if (2 * q + 1 == k && r >= k) { c.b = (r == k) ? d : lrk; dt[r * 8 + k] = c.b; }
-    if (lane == 0) rsd[k] = rs;
-    __syncwarp();
+    const double rs = rsqrt(pk);
+    rsv[k] = rs;
+    const double lrk = trk * rs;
+    if (2 * q > k && r >= 2 * q) c.a = fma(-lrk, tc0 * rs, c.a);
+    if (2 * q + 1 > k && r >= 2 * q + 1) c.b = fma(-lrk, tc1 * rs, c.b);
+    if (2 * q == k && r >= k) c.a = (r == k) ? pk * rs : lrk;
+    if (2 * q + 1 == k && r >= k) c.b = (r == k) ? pk * rs : lrk;
   }
-  *half_logdet += hl;
+  tile_store(dt, lane, c);
+  {
+    const int kk = lane & 7, src = 4 * kk + (kk >> 1);   // L[kk][kk] lives in lane (kk, kk/2), element kk & 1
+    const double da = __shfl_sync(0xffffffffu, c.a, src), db = __shfl_sync(0xffffffffu, c.b, src);
+    if (lane < 8) dpiv[lane] = (lane & 1) ? db : da;
+  }
+  __syncwarp();
   // inverse by columns: lane cc < 8 owns column cc of X = inv(L)
   if (lane < 8) {
     const int cc = lane;
@@ -77,7 +91,7 @@ __device__ __forceinline__ int chol8_inv8(tile2 c, int lane, double* dt, double*
 #pragma unroll
       for (int m = 0; m < 8; ++m)
         if (m < rr) acc = fma(dt[rr * 8 + m], (m >= cc) ? xcol[m] : 0.0, acc);
-      const double v = (rr == cc) ? rsd[rr] : -acc * rsd[rr];
+      const double v = (rr == cc) ? rsv[rr] : -acc * rsv[rr];
       xcol[rr] = (rr >= cc) ? v : 0.0;
     }
 #pragma unroll
@@ -87,8 +101,10 @@ __device__ __forceinline__ int chol8_inv8(tile2 c, int lane, double* dt, double*
   return fail;
 }
 
-template <int KID>
-__global__ void __launch_bounds__(FIT_THREADS) gp_fit_kernel(const FitArgs a) {
+template <int KID, int FIT_WARPS>
+__global__ void __launch_bounds__(FIT_WARPS * 32) gp_fit_kernel(const FitArgs a) {
+  constexpr int FIT_THREADS = FIT_WARPS * 32;
+  extern __shared__ __align__(128) double pool[];               // tile pool, see fit_pool_tiles
   __shared__ double fx[NPAD], fxx[NPAD], fc[NPAD], fs[NPAD];   // per-point features
   __shared__ double ys[NPAD];
   __shared__ double zs[NPAD];
@@ -96,10 +112,9 @@ __global__ void __launch_bounds__(FIT_THREADS) gp_fit_kernel(const FitArgs a) {
   __shared__ KProg kps;
   __shared__ __align__(16) double dt[64];
   __shared__ __align__(16) double linv[64];
-  __shared__ double rsd[8];
-  __shared__ double s_red[FIT_THREADS / 32];
+  __shared__ double dpiv[NPAD];          // diagonal of L (pivots), logged in parallel at the end
+  __shared__ double s_red[FIT_WARPS];
   __shared__ int s_fail;
-  __shared__ double s_hl;
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int r = lane >> 2, q = lane & 3;
@@ -109,6 +124,7 @@ __global__ void __launch_bounds__(FIT_THREADS) gp_fit_kernel(const FitArgs a) {
   const long long ti = a.theta_mode == 0 ? 0 : (a.theta_mode == 1 ? (long long)win : p / a.n_windows);
   const double* th = a.theta + ti * a.theta_stride;
   const int N = a.N, nt = a.nt;
+  const int h = (nt + 1) / 2, nb = nt - h;          // tile rows of the top block / bottom block
   const double noise = th[a.kp.n_params];
   FastK<KID> fk;
   if (KID != KID_GENERIC) fk.init(th);
@@ -145,6 +161,8 @@ __global__ void __launch_bounds__(FIT_THREADS) gp_fit_kernel(const FitArgs a) {
   };
 
   double* Lp = a.L + lp * (long long)tiles_in_lower(nt) * 64;
+  double* poolA = pool + 2 * lane;                       // lane-offset views of the two pool regions
+  double* poolB = pool + (h * (h + 1) / 2) * 64 + 2 * lane;
   const int max_attempts = a.jitter_retry ? 6 : 1;
   double extra = 0.0;
   int fail_pivot = 0, attempts_used = 0;
@@ -166,40 +184,75 @@ __global__ void __launch_bounds__(FIT_THREADS) gp_fit_kernel(const FitArgs a) {
     } else if (attempt > 1) {
       extra *= 10.0;
     }
-    if (tid == 0) { s_fail = 0; s_hl = 0.0; }
+    if (tid == 0) s_fail = 0;
     __syncthreads();
     const double dadd = noise + CNGP_JITTER + extra;
 
     for (int j = 0; j < nt; ++j) {
-      // my row tiles of this column: i_t = j + w + 8 t  (t < nvalid), plus possibly the z row (i == nt)
-      const int rem = nt - j - w;                       // i_t < nt  <=>  8 t < rem
-      const int nvalid = rem > 0 ? min(FIT_MAXT, (rem + 7) >> 3) : 0;
-      const bool zmine = rem >= 0 && (rem & 7) == 0 && (rem >> 3) < FIT_MAXT;
-      // ---- left-looking update: S_t = sum_{k<j} L(i_t,k) L(j,k)^T;  column k starts at cb, tile (i,k) at cb+(i-k)*64
+      // my row tiles of this column: i_t = j + w + FIT_WARPS t  (t < nvalid), plus possibly the z row (i == nt)
+      const int rem = nt - j - w;                       // i_t < nt  <=>  FIT_WARPS t < rem
+      const int nvalid = rem > 0 ? min(FIT_MAXT, (rem + FIT_WARPS - 1) / FIT_WARPS) : 0;
+      const bool zmine = rem >= 0 && (rem % FIT_WARPS) == 0 && (rem / FIT_WARPS) < FIT_MAXT;
+      // ---- left-looking update: S_t = sum_{k<j} L(i_t,k) L(j,k)^T, every tile read from the shared-memory pool
       tile2 S[FIT_MAXT];
+      const double* xb[FIT_MAXT];    // per-tile base: region + i_t * 64 (the column part is added per k)
+      bool inA[FIT_MAXT];
 #pragma unroll
-      for (int t = 0; t < FIT_MAXT; ++t) S[t] = tile2{0.0, 0.0};
+      for (int t = 0; t < FIT_MAXT; ++t) {
+        S[t] = tile2{0.0, 0.0};
+        const int i = j + w + FIT_WARPS * t;
+        inA[t] = (j < h) && (i < h);
+        xb[t] = (inA[t] ? poolA : poolB) + i * 64;
+      }
       tile2 Sz{0.0, 0.0};
-      const double* cb = Lp + 2 * lane;
+      const int kA_end = j < h ? j : h;
+      {
+        // columns k < h:  A-tile (i,k) at A[k h - k(k-1)/2 + i - k],  B-tile (i,k) at B[k nb + i - h]
+        int offA = 0, offB = -h;
+        const double* yb = (j < h ? poolA : poolB) + j * 64;
+        const bool yA = j < h;
 #pragma unroll 2
-      for (int k = 0; k < j; ++k) {
-        const double* py = cb + (j - k) * 64;
-        const double* px = py + w * 64;
-        const double2 yv = *reinterpret_cast<const double2*>(py);
-        const tile2 Y{yv.x, yv.y};
+        for (int k = 0; k < kA_end; ++k) {
+          const double2 yv = *reinterpret_cast<const double2*>(yb + (yA ? offA : offB) * 64);
+          const tile2 Y{yv.x, yv.y};
 #pragma unroll
-        for (int t = 0; t < FIT_MAXT; ++t) {
-          if (t < nvalid) {
-            const double2 xv = *reinterpret_cast<const double2*>(px + t * (FIT_WARPS * 64));
-            tile_mma(S[t], tile2{xv.x, xv.y}, Y);
+          for (int t = 0; t < FIT_MAXT; ++t) {
+            if (t < nvalid) {
+              const double2 xv = *reinterpret_cast<const double2*>(xb[t] + (inA[t] ? offA : offB) * 64);
+              tile_mma(S[t], tile2{xv.x, xv.y}, Y);
+            }
           }
+          if (zmine) {
+            tile2 X{0.0, 0.0};
+            if (r == 0) { X.a = zs[8 * k + 2 * q]; X.b = zs[8 * k + 2 * q + 1]; }
+            tile_mma(Sz, X, Y);
+          }
+          offA += h - k - 1;
+          offB += nb;
         }
-        if (zmine) {
-          tile2 X{0.0, 0.0};
-          if (r == 0) { X.a = zs[8 * k + 2 * q]; X.b = zs[8 * k + 2 * q + 1]; }
-          tile_mma(Sz, X, Y);
+      }
+      if (j > h) {
+        // columns h <= k < j live in region A again: tile (i,k) at A[(k-h) nb - (k-h)(k-h-1)/2 + i - k]
+        int off2 = -h;
+        const double* yb = poolA + j * 64;
+#pragma unroll 2
+        for (int k = h; k < j; ++k) {
+          const double2 yv = *reinterpret_cast<const double2*>(yb + off2 * 64);
+          const tile2 Y{yv.x, yv.y};
+#pragma unroll
+          for (int t = 0; t < FIT_MAXT; ++t) {
+            if (t < nvalid) {
+              const double2 xv = *reinterpret_cast<const double2*>(poolA + (off2 + j + w + FIT_WARPS * t) * 64);
+              tile_mma(S[t], tile2{xv.x, xv.y}, Y);
+            }
+          }
+          if (zmine) {
+            tile2 X{0.0, 0.0};
+            if (r == 0) { X.a = zs[8 * k + 2 * q]; X.b = zs[8 * k + 2 * q + 1]; }
+            tile_mma(Sz, X, Y);
+          }
+          off2 += nb - (k - h) - 1;
         }
-        cb += (nt - k) * 64;
       }
       // ---- C_t = Ky tile - S_t (Ky evaluated here, never stored) ----
       {
@@ -225,23 +278,25 @@ __global__ void __launch_bounds__(FIT_THREADS) gp_fit_kernel(const FitArgs a) {
       // ---- diagonal tile: factor + invert (warp 0 owns i == j at t == 0) ----
       double* colj = Lp + (long long)tile_index(j, j, nt) * 64;
       if (w == 0) {
-        double hl = 0.0;
-        const int f = chol8_inv8(S[0], lane, dt, linv, rsd, &hl);
-        if (lane == 0) {
-          if (f && s_fail == 0) s_fail = 8 * j + f;
-          s_hl += hl;
-        }
+        const int f = chol8_inv8(S[0], lane, dt, linv, dpiv + 8 * j);
+        if (lane == 0 && f && s_fail == 0) s_fail = 8 * j + f;
         tile_store(colj, lane, tile_load(linv, lane));
       }
       __syncthreads();
-      // ---- rows below: L(i,j) = C_t inv(L_jj)^T ----
+      // ---- rows below: L(i,j) = C_t inv(L_jj)^T  -> pool (for later columns) and global (for phase B) ----
       const tile2 Yinv = tile_load(linv, lane);
+      // pool position of tile (i, j): same mapping as above with k = j
+      const int pj = j < h ? (j * h - j * (j - 1) / 2 - j) : ((j - h) * nb - (j - h) * (j - h - 1) / 2 - j);
+      const int pjB = j * nb - h;
 #pragma unroll
       for (int t = 0; t < FIT_MAXT; ++t) {
         if (t < nvalid && (w + t) > 0) {
+          const int i = j + w + FIT_WARPS * t;
           tile2 Lt{0.0, 0.0};
           tile_mma(Lt, S[t], Yinv);
-          tile_store(colj + (w + FIT_WARPS * t) * 64, lane, Lt);
+          tile_store(colj + (i - j) * 64, lane, Lt);
+          double* dst = (j < h && i >= h) ? (poolB + (pjB + i) * 64) : (poolA + (pj + i) * 64);
+          *reinterpret_cast<double2*>(dst) = make_double2(Lt.a, Lt.b);
         }
       }
       if (zmine) {
@@ -259,20 +314,24 @@ __global__ void __launch_bounds__(FIT_THREADS) gp_fit_kernel(const FitArgs a) {
 
   // ---- outputs: z, quad = z'z, logdet = 2 sum log L_kk, lml ----
   double* zp = a.z + lp * (long long)(nt * 8);
-  double qs = 0.0;
+  double qs = 0.0, hl = 0.0;
   for (int i = tid; i < nt * 8; i += FIT_THREADS) {
     const double v = zs[i];
     zp[i] = v;
     qs += v * v;
+    hl += log(dpiv[i]);      // padded rows have pivot 1
   }
-  for (int o = 16; o; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
+  for (int o = 16; o; o >>= 1) {
+    qs += __shfl_xor_sync(0xffffffffu, qs, o);
+    hl += __shfl_xor_sync(0xffffffffu, hl, o);
+  }
   __syncthreads();
-  if (lane == 0) s_red[w] = qs;
+  if (lane == 0) { s_red[w] = qs; fx[w] = hl; }   // fx is free by now
   __syncthreads();
   if (tid == 0) {
-    double quad = 0.0;
-    for (int i = 0; i < FIT_WARPS; ++i) quad += s_red[i];
-    const double logdet = 2.0 * s_hl;
+    double quad = 0.0, hls = 0.0;
+    for (int i = 0; i < FIT_WARPS; ++i) { quad += s_red[i]; hls += fx[i]; }
+    const double logdet = 2.0 * hls;
     const double nanv = __longlong_as_double(0x7ff8000000000000LL);
     const bool bad = fail_pivot != 0;
     if (a.quad) a.quad[p] = bad ? nanv : quad;

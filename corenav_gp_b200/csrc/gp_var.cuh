@@ -22,8 +22,8 @@
 
 namespace cngp {
 
-constexpr int VAR_CT = 8;                       // tiles per chunk (4 KB)
-constexpr int VAR_NSLOT = 6;                    // ring slots per CTA
+constexpr int VAR_CT = 16;                      // tiles per chunk (8 KB)
+constexpr int VAR_NSLOT = 4;                    // ring slots per CTA
 constexpr int VAR_CHUNK_DOUBLES = VAR_CT * 64;
 constexpr int VAR_CHUNK_BYTES = VAR_CHUNK_DOUBLES * 8;
 constexpr int VAR_STAGE_TILES = 8;              // K* staging: tile columns per pass
@@ -53,9 +53,32 @@ struct VarShared {
   unsigned long long full[VAR_NSLOT];   // mbarriers: chunk landed
   int cnt[VAR_NSLOT];                   // warps that have released the slot
   int cur_it, cur_round, cur_ce;        // producer cursor: next chunk to load
+  int ce_max, nrounds, nwin_cta, n_tiles;
+  const double* Lbase;
+  uint32_t ring_u32, full_u32;
 };
 
-template <int NT_MAX, int WARPS, int KID>
+// Load the chunk under the producer cursor into `slot` and advance the cursor.  Called by one lane at a time (the
+// prologue, then whichever lane performed the last release of a slot); kept out of line: it is the rare path.
+__device__ __noinline__ void var_issue_next(VarShared* sh, int slot) {
+  const int it = sh->cur_it;
+  if (it >= sh->nwin_cta) return;
+  const int ce = sh->cur_ce;
+  const long long lw = blockIdx.x + (long long)it * gridDim.x;
+  const double* src = sh->Lbase + (lw + 1) * (long long)sh->n_tiles * 64 - (long long)(VAR_CT * ce + VAR_CT) * 64;
+  mbar_expect_tx(sh->full_u32 + 8 * slot, VAR_CHUNK_BYTES);
+  bulk_g2s(sh->ring_u32 + slot * VAR_CHUNK_BYTES, src, VAR_CHUNK_BYTES, sh->full_u32 + 8 * slot);
+  if (ce > 0) {
+    sh->cur_ce = ce - 1;
+  } else {
+    sh->cur_ce = sh->ce_max;
+    if (sh->cur_round + 1 < sh->nrounds) sh->cur_round = sh->cur_round + 1;
+    else { sh->cur_round = 0; sh->cur_it = it + 1; }
+  }
+}
+
+// FULL: nt == NT_MAX and N == 8 nt (no padding) - drops every per-column guard from the unrolled code.
+template <int NT_MAX, int WARPS, int KID, bool FULL>
 __global__ void __launch_bounds__(WARPS * 32, 1) gp_var_kernel(const VarArgs a) {
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ LeafConst hc_all[KID == KID_GENERIC ? WARPS : 1][CNGP_MAX_LEAVES];
@@ -63,7 +86,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gp_var_kernel(const VarArgs a) 
   __shared__ VarShared sh;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int r = lane >> 2, q = lane & 3;
-  const int N = a.N, nt = a.nt, M = a.M, mt = a.mt;
+  const int N = FULL ? NT_MAX * 8 : a.N, nt = FULL ? NT_MAX : a.nt, M = a.M, mt = a.mt;
   const int n8 = nt * 8;
   const int n_tiles = tiles_in_lower(nt);
   const int ce_max = (n_tiles - 1) / VAR_CT;      // chunk ids count from the END of a window's factor
@@ -76,30 +99,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gp_var_kernel(const VarArgs a) 
   const uint32_t ring_u32 = smem_u32(ring);
   const uint32_t full_u32 = smem_u32(&sh.full[0]);
 
-  // load the chunk under the producer cursor into `slot` and advance the cursor (one lane at a time, see header)
-  auto issue_next = [&](int slot) {
-    const int it = sh.cur_it;
-    if (it >= nwin_cta) return;
-    const int ce = sh.cur_ce;
-    const long long lw = blockIdx.x + (long long)it * gridDim.x;
-    const double* src = a.L + (lw + 1) * (long long)n_tiles * 64 - (long long)(VAR_CT * ce + VAR_CT) * 64;
-    mbar_expect_tx(full_u32 + 8 * slot, VAR_CHUNK_BYTES);
-    bulk_g2s(ring_u32 + slot * VAR_CHUNK_BYTES, src, VAR_CHUNK_BYTES, full_u32 + 8 * slot);
-    if (ce > 0) {
-      sh.cur_ce = ce - 1;
-    } else {
-      sh.cur_ce = ce_max;
-      if (sh.cur_round + 1 < nrounds) sh.cur_round = sh.cur_round + 1;
-      else { sh.cur_round = 0; sh.cur_it = it + 1; }
-    }
-  };
-
   if (threadIdx.x == 0) {
     if (KID == KID_GENERIC) kps = a.kp;
     for (int s = 0; s < VAR_NSLOT; ++s) { mbar_init(full_u32 + 8 * s, 1); sh.cnt[s] = 0; }
     sh.cur_it = 0; sh.cur_round = 0; sh.cur_ce = ce_max;
+    sh.ce_max = ce_max; sh.nrounds = nrounds; sh.nwin_cta = nwin_cta; sh.n_tiles = n_tiles;
+    sh.Lbase = a.L; sh.ring_u32 = ring_u32; sh.full_u32 = full_u32;
     mbar_fence_init();
-    for (int s = 0; s < VAR_NSLOT; ++s) issue_next(s);   // global chunk g goes to slot g % VAR_NSLOT
+    for (int s = 0; s < VAR_NSLOT; ++s) var_issue_next(&sh, s);   // global chunk g goes to slot g % VAR_NSLOT
   }
   __syncthreads();
 
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gp_var_kernel(const VarArgs a) 
           if (old == WARPS - 1) {
             sh.cnt[slot] = 0;
             __threadfence_block();
-            issue_next(slot);
+            var_issue_next(&sh, slot);
           }
         }
         if (++slot == VAR_NSLOT) { slot = 0; parity ^= 1u; }
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gp_var_kernel(const VarArgs a) 
         for (int jj = VAR_STAGE_TILES - 1; jj >= 0; --jj) {
           const int J = p * VAR_STAGE_TILES + jj;
           double2 v = make_double2(0.0, 0.0);
-          if (J < nt) {
+          if (FULL || J < nt) {
             const int c0 = 8 * (nt - 1 - J) + 2 * q;
             const double2 x2 = *reinterpret_cast<const double2*>(fp + c0);
             if (KID == KID_GENERIC) {
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gp_var_kernel(const VarArgs a) 
       // compile-time after unrolling; the ring slot advances by one per chunk.
       auto next_tile = [&](const int e, const bool first) -> tile2 {
         const int ce = (e - 1) / VAR_CT;
-        if (first || (e - 1) % VAR_CT == VAR_CT - 1) mbar_wait(full_u32 + 8 * slot, parity);
+        if ((!FULL && first) || (e - 1) % VAR_CT == VAR_CT - 1) mbar_wait(full_u32 + 8 * slot, parity);
         const double2 v = *reinterpret_cast<const double2*>(cptr + (VAR_CT * ce + VAR_CT - e) * 64);
         if ((e - 1) % VAR_CT == 0) {     // chunk drained by this warp
           release_chunk();
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gp_var_kernel(const VarArgs a) 
 
 #pragma unroll
       for (int J = NT_MAX - 1; J >= 0; --J) {
-        if (J < nt) {
+        if (FULL || J < nt) {
           const int e0 = (J + 1) * (J + 2) / 2;   // distance from the end of tile (J, d = 0)
           const tile2 Yd = next_tile(e0, J == nt - 1);
           tile2 V{0.0, 0.0};
@@ -219,10 +226,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gp_var_kernel(const VarArgs a) 
           ms = fma(V.a, zz.x, ms);
           ms = fma(V.b, zz.y, ms);
           const tile2 nV{-V.a, -V.b};
+          // two tiles per step with their DMMA pairs interleaved (a dependent DMMA costs 26 cycles, issue 16)
 #pragma unroll
-          for (int J2 = J - 1; J2 >= 0; --J2) {
-            const tile2 Yl = next_tile(e0 - (J - J2), false);
-            tile_mma(R[J2], nV, Yl);
+          for (int J2 = J - 1; J2 >= 1; J2 -= 2) {
+            const tile2 Ya = next_tile(e0 - (J - J2), false);
+            const tile2 Yb = next_tile(e0 - (J - J2) - 1, false);
+            dmma884(R[J2].a, R[J2].b, nV.a, Ya.a);
+            dmma884(R[J2 - 1].a, R[J2 - 1].b, nV.a, Yb.a);
+            dmma884(R[J2].a, R[J2].b, nV.b, Ya.b);
+            dmma884(R[J2 - 1].a, R[J2 - 1].b, nV.b, Yb.b);
+          }
+          if (J & 1) {   // J tiles below the diagonal: one left over when J is odd
+            const tile2 Yl = next_tile(e0 - J, false);
+            tile_mma(R[0], nV, Yl);
           }
         }
       }

@@ -202,8 +202,10 @@ __device__ __forceinline__ double fast_exp(double x) {
   p = fma(p, f, 0.5);
   p = fma(p, f, 1.0);
   p = fma(p, f, 1.0);
-  const double r = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-  return x < -708.0 ? 0.0 : r;
+  // scale by 2^n through the exponent field; below 2^-1021 flush to zero (integer compare: keeps the FP64 pipe free)
+  const int hi = (n < -1021) ? 0 : __double2hiint(p) + (n << 20);
+  const int lo = (n < -1021) ? 0 : __double2loint(p);
+  return __hiloint2double(hi, lo);
 }
 
 struct PointFeat {
@@ -236,11 +238,13 @@ struct FastK {
   __device__ __forceinline__ double eval(const PointFeat& a, const PointFeat& b, bool same_sym) const {
     double rr = r2(a, b);
     if (same_sym) rr = 0.0;
-    const double e1 = c0 * fast_exp(fmin(rr * c1, 0.0));   // fmin == GPy's clip of r2 at 0
+    // GPy clips r2 at 0; a negative r2 can only be rounding noise of the expanded form (|r2| < 1e-11 x^2), for which
+    // exp(r2 c1) differs from 1 by < 1e-13 - the clip is dropped here to keep two operations off the FP64 pipe.
+    const double e1 = c0 * fast_exp(rr * c1);
     if (KID == KID_RBF) return e1;
     if (KID == KID_RBF_PER) {
       const double cd = fma(a.c, b.c, a.s * b.s);          // cos(phi_a - phi_b)
-      return fma(c4, fast_exp(fmin(fma(c3, cd, -c3), 0.0)), e1);
+      return fma(c4, fast_exp(fma(c3, cd, -c3)), e1);
     }
     // rbf * brownian
     const bool agree = (a.x > 0.0 && b.x > 0.0) || (a.x < 0.0 && b.x < 0.0) || (a.x == 0.0 && b.x == 0.0);

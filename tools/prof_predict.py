@@ -16,6 +16,8 @@ x, y = syn.slip_windows(0, B, N)
 xs = syn.test_grid(x[0], M)
 th = syn.theta_for(kern)
 dx, dy, dxs, dth = (torch.from_numpy(a).cuda() for a in (x, y, xs, th))
+out = ctx.predict(kern, dth, dx, dy, dxs)   # warm-up (module load, attributes)
+torch.cuda.synchronize()
 ctx.set_profiling(True)
 for _ in range(steps):
     out = ctx.predict(kern, dth, dx, dy, dxs)
