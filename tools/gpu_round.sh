@@ -1,0 +1,17 @@
+#!/bin/bash
+# One GPU-box round: parity tests, smoke, bench, ncu launch list, ncu full captures of the two predict kernels.
+# usage (under gpurun): bash tools/gpu_round.sh [tag]
+TAG=${1:-r01}
+O=gpurun_out
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $O/smi_$TAG.csv 2>&1
+timeout 1200 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu_$TAG.log
+timeout 300 python __graft_entry__.py --smoke > $O/smoke_$TAG.log 2>&1; echo "smoke rc=$?" >> $O/smoke_$TAG.log
+timeout 900 python bench.py --steps 10 --warmup 3 > $O/bench_$TAG.json 2> $O/bench_$TAG.err; echo "bench rc=$?" >> $O/bench_$TAG.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/launches_$TAG.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_under_ncu_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gp_var -s 1 -c 1 -f -o $O/prof_var_$TAG \
+    python tools/prof_predict.py 4096 256 600 1 > $O/ncu_var_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gp_fit -s 1 -c 1 -f -o $O/prof_fit_$TAG \
+    python tools/prof_predict.py 4096 256 600 1 > $O/ncu_fit_$TAG.log 2>&1
+tail -3 $O/pytest_gpu_$TAG.log; tail -2 $O/smoke_$TAG.log; cat $O/bench_$TAG.json | cut -c1-1500; tail -2 $O/bench_$TAG.err
