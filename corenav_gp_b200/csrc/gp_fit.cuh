@@ -32,7 +32,9 @@ struct FitArgs {
   KProg kp;
   const double* theta;   // hyper-parameters, noise last
   long long theta_stride;
-  int theta_mode;        // 0 shared, 1 per window (problem % n_windows), 2 per candidate (problem / n_windows)
+  int theta_mode;        // 0 shared, 1 per window (problem % n_windows), 2 per candidate (problem / n_windows),
+                         // 3 per problem (theta row = problem; the window comes from win_map)
+  const int* win_map;    // [n_problems] window of each problem (theta_mode 3), or null
   const double* x;       // [n_windows][N]
   const double* y;       // [n_windows][N]
   int N, nt;             // nt = ceil(N / 8)
@@ -120,8 +122,8 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) gp_fit_kernel(const FitArgs a)
   const int r = lane >> 2, q = lane & 3;
   const long long lp = blockIdx.x;                 // problem within this launch
   const long long p = a.problem0 + lp;             // global problem
-  const int win = (int)(p % a.n_windows);
-  const long long ti = a.theta_mode == 0 ? 0 : (a.theta_mode == 1 ? (long long)win : p / a.n_windows);
+  const int win = a.win_map ? a.win_map[p] : (int)(p % a.n_windows);
+  const long long ti = a.theta_mode == 0 ? 0 : (a.theta_mode == 1 ? (long long)win : (a.theta_mode == 3 ? p : p / a.n_windows));
   const double* th = a.theta + ti * a.theta_stride;
   const int N = a.N, nt = a.nt;
   const int h = (nt + 1) / 2, nb = nt - h;          // tile rows of the top block / bottom block

@@ -22,8 +22,9 @@ constexpr int GRAD_THREADS = GRAD_WARPS * 32;
 
 struct GradArgs {
   KProg kp;
-  const double* theta;     // [C][P]
+  const double* theta;     // [C][P]  (or [n_problems][P] when win_map is given)
   long long theta_stride;  // P
+  const int* win_map;      // [n_problems] window of each problem - theta row = problem - or null
   const double* x;         // [n_windows][N]
   int N, nt, n_windows;
   long long problem0;
@@ -52,8 +53,8 @@ __global__ void __launch_bounds__(GRAD_THREADS) gp_grad_kernel(const GradArgs a)
   const int r = lane >> 2, q = lane & 3;
   const long long lp = blockIdx.x;
   const long long p = a.problem0 + lp;
-  const int win = (int)(p % a.n_windows);
-  const long long cand = p / a.n_windows;
+  const int win = a.win_map ? a.win_map[p] : (int)(p % a.n_windows);
+  const long long cand = a.win_map ? p : p / a.n_windows;
   const double* th = a.theta + cand * a.theta_stride;
   const int N = a.N, nt = a.nt, P = a.kp.n_params + 1;
   const double* Lp = a.L + lp * (long long)tiles_in_lower(nt) * 64;

@@ -47,6 +47,7 @@ struct VarArgs {
   const int* status;       // [n_windows] (phase A), may be null
   double* mean;            // [n_windows][M]
   double* var;             // [n_windows][M]
+  int sigma_mode;          // 0: var;  1: write sigma = 2 sqrt(var) instead (gp_slip_node.py:61)
 };
 
 struct VarShared {
@@ -250,7 +251,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gp_var_kernel(const VarArgs a) 
         const double kss = (KID == KID_GENERIC) ? kdiag_eval(kps, hc, xm) : fk.kdiag(xm);
         const double nanv = __longlong_as_double(0x7ff8000000000000LL);
         a.mean[win * M + m] = bad ? nanv : ms;
-        a.var[win * M + m] = bad ? nanv : fmax(kss - vs, CNGP_VAR_FLOOR) + noise;
+        const double vv = fmax(kss - vs, CNGP_VAR_FLOOR) + noise;
+        a.var[win * M + m] = bad ? nanv : (a.sigma_mode ? 2.0 * sqrt(vv) : vv);
       }
     }
   }
