@@ -50,6 +50,8 @@ SIGNATURES = {
                                      c_i32, c_dp, c_dp, c_dp, c_ip, c_i32]),
     "cngp_lml_grad_batch": (C.c_int, [c_vp, C.POINTER(Kernel), c_dp, c_i64, c_dp, c_dp, c_i64, c_i32, c_dp, c_dp,
                                       c_ip, c_i32]),
+    "cngp_lml_grad_windows": (C.c_int, [c_vp, C.POINTER(Kernel), c_dp, c_i64, c_ip, c_dp, c_dp, c_i64, c_i32, c_dp,
+                                        c_dp, c_ip, c_i32]),
     "cngp_optimize_batch": (C.c_int, [c_vp, C.POINTER(Kernel), c_dp, c_i64, c_dp, c_dp, c_i64, c_i32, c_i32, c_dp,
                                       c_dp, c_ip]),
     "cngp_gp_slip_batch": (C.c_int, [c_vp, C.POINTER(Kernel), c_dp, c_i64, c_dp, c_dp, c_i64, c_i32, c_i32, c_i32,

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "cngp_internal.h"
 #include "gp_fit.cuh"
 #include "gp_grad.cuh"
 #include "gp_var.cuh"
@@ -100,6 +101,8 @@ static int fail(cngp_ctx* c, int code, const char* fmt, ...) {
   if (c) c->err = tmp; else g_create_error = tmp;
   return code;
 }
+
+int cngp_set_error(cngp_ctx* ctx, int code, const char* text) { return fail(ctx, code, "%s", text); }
 
 #define CU(c, call)                                                                                  \
   do {                                                                                               \
@@ -418,10 +421,9 @@ static void launch_fit(int kid, const FitArgs& fa, long long nprob, cudaStream_t
   }
 }
 
-extern "C" int cngp_predict_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t theta_stride,
-                                  const double* x, const double* y, const double* xstar, int64_t xstar_stride,
-                                  int64_t B, int32_t N, int32_t M, double* mean, double* var, double* lml,
-                                  int32_t* status, int32_t mem) {
+int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t theta_stride,
+                      const double* x, const double* y, const double* xstar, int64_t xstar_stride, int64_t B, int32_t N,
+                      int32_t M, double* mean, double* var, double* lml, int32_t* status, int32_t mem, int sigma_mode) {
   if (!ctx) return CNGP_ERR_INVALID;
   if (!kernel || !theta || !x || !y || B < 0 || N <= 0 || M < 0) return fail(ctx, CNGP_ERR_INVALID, "predict: bad argument");
   if (M > 0 && (!xstar || !mean || !var)) return fail(ctx, CNGP_ERR_INVALID, "predict: xstar/mean/var null");
@@ -463,6 +465,7 @@ extern "C" int cngp_predict_batch(cngp_ctx* ctx, const cngp_kernel* kernel, cons
     FitArgs fa;
     fa.kp = kp;
     fa.theta = d_theta; fa.theta_stride = theta_stride; fa.theta_mode = theta_stride ? 1 : 0;
+    fa.win_map = nullptr;
     fa.x = d_x; fa.y = d_y; fa.N = N; fa.nt = nt; fa.n_windows = (int)B; fa.problem0 = w0;
     fa.L = Lbuf; fa.z = zbuf; fa.feat = fbuf; fa.lml = d_lml; fa.logdet = nullptr; fa.quad = nullptr;
     fa.status = d_status;
@@ -477,6 +480,7 @@ extern "C" int cngp_predict_batch(cngp_ctx* ctx, const cngp_kernel* kernel, cons
       va.xstar = d_xs; va.xstar_stride = xstar_stride;
       va.N = N; va.nt = nt; va.M = M; va.mt = mt; va.window0 = w0; va.n_windows_launch = nw;
       va.L = Lbuf; va.z = zbuf; va.feat = fbuf; va.status = d_status; va.mean = d_mean; va.var = d_var;
+      va.sigma_mode = sigma_mode;
       ctx->begin(CNGP_PROF_VAR);
       if (nt <= 8) launch_var<8, 16>(kid, va, nw, ctx->stream);
       else if (nt <= 16) launch_var<16, 16>(kid, va, nw, ctx->stream);
@@ -490,12 +494,21 @@ extern "C" int cngp_predict_batch(cngp_ctx* ctx, const cngp_kernel* kernel, cons
   return CNGP_OK;
 }
 
+extern "C" int cngp_predict_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t theta_stride,
+                                  const double* x, const double* y, const double* xstar, int64_t xstar_stride,
+                                  int64_t B, int32_t N, int32_t M, double* mean, double* var, double* lml,
+                                  int32_t* status, int32_t mem) {
+  return cngp_predict_impl(ctx, kernel, theta, theta_stride, x, y, xstar, xstar_stride, B, N, M, mean, var, lml, status,
+                           mem, 0);
+}
+
 // ------------------------------------------------------------------------------------------------------------
-// LML + gradient for C candidates x B windows
+// LML + gradient for C candidates x B windows (win_map == null), or for n_prob independent (theta row, window)
+// problems: problem p uses theta row p and window win_map[p] of the B windows (C = n_prob then).
 // ------------------------------------------------------------------------------------------------------------
-extern "C" int cngp_lml_grad_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t C,
-                                   const double* x, const double* y, int64_t B, int32_t N, double* lml, double* grad,
-                                   int32_t* status, int32_t mem) {
+int cngp_lml_grad_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t C, const double* x,
+                       const double* y, int64_t B, int32_t N, double* lml, double* grad, int32_t* status, int32_t mem,
+                       const int32_t* win_map) {
   if (!ctx) return CNGP_ERR_INVALID;
   if (!kernel || !theta || !x || !y || C < 0 || B < 0 || N <= 0) return fail(ctx, CNGP_ERR_INVALID, "lml_grad: bad argument");
   if (N > CNGP_MAX_N) return fail(ctx, CNGP_ERR_UNSUPPORTED, "lml_grad: N=%d > %d", N, CNGP_MAX_N);
@@ -506,12 +519,13 @@ extern "C" int cngp_lml_grad_batch(cngp_ctx* ctx, const cngp_kernel* kernel, con
   const int P = kp.n_params + 1;
   CU(ctx, cudaSetDevice(ctx->cfg.device));
   if ((rc = ensure_scratch(ctx))) return rc;
-  const long long n_prob = (long long)C * B;
+  const long long n_prob = win_map ? (long long)C : (long long)C * B;
 
   Stage st{ctx, mem};
   const double* d_theta = (const double*)st.in(theta, sizeof(double) * (size_t)C * P);
   const double* d_x = (const double*)st.in(x, sizeof(double) * (size_t)B * N);
   const double* d_y = (const double*)st.in(y, sizeof(double) * (size_t)B * N);
+  const int* d_map = (const int*)st.in(win_map, sizeof(int) * (size_t)n_prob);
   double* d_lml = (double*)st.out(lml, sizeof(double) * (size_t)n_prob);
   double* d_grad = (double*)st.out(grad, sizeof(double) * (size_t)n_prob * P);
   int* d_status = (int*)st.out(status, sizeof(int) * (size_t)n_prob);
@@ -533,7 +547,8 @@ extern "C" int cngp_lml_grad_batch(cngp_ctx* ctx, const cngp_kernel* kernel, con
     double* abuf = zbuf + (size_t)np * nt * 8;
     FitArgs fa;
     fa.kp = kp;
-    fa.theta = d_theta; fa.theta_stride = P; fa.theta_mode = 2;
+    fa.theta = d_theta; fa.theta_stride = P; fa.theta_mode = d_map ? 3 : 2;
+    fa.win_map = d_map;
     fa.x = d_x; fa.y = d_y; fa.N = N; fa.nt = nt; fa.n_windows = (int)B; fa.problem0 = p0;
     fa.L = Lbuf; fa.z = zbuf; fa.feat = nullptr; fa.lml = d_lml; fa.logdet = nullptr; fa.quad = nullptr;
     fa.status = d_status;
@@ -544,7 +559,7 @@ extern "C" int cngp_lml_grad_batch(cngp_ctx* ctx, const cngp_kernel* kernel, con
     if (grad) {
       GradArgs ga;
       ga.kp = kp;
-      ga.theta = d_theta; ga.theta_stride = P;
+      ga.theta = d_theta; ga.theta_stride = P; ga.win_map = d_map;
       ga.x = d_x; ga.N = N; ga.nt = nt; ga.n_windows = (int)B; ga.problem0 = p0;
       ga.L = Lbuf; ga.W = Wbuf; ga.z = zbuf; ga.alpha = abuf; ga.status = d_status; ga.grad = d_grad;
       ctx->begin(CNGP_PROF_GRAD);
@@ -556,6 +571,19 @@ extern "C" int cngp_lml_grad_batch(cngp_ctx* ctx, const cngp_kernel* kernel, con
   rc = st.finish();
   if (rc) return fail(ctx, rc, "lml_grad: copy-out failed: %s", cudaGetErrorString(cudaGetLastError()));
   return CNGP_OK;
+}
+
+extern "C" int cngp_lml_grad_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t C,
+                                   const double* x, const double* y, int64_t B, int32_t N, double* lml, double* grad,
+                                   int32_t* status, int32_t mem) {
+  return cngp_lml_grad_impl(ctx, kernel, theta, C, x, y, B, N, lml, grad, status, mem, nullptr);
+}
+
+extern "C" int cngp_lml_grad_windows(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t n_problems,
+                                     const int32_t* window_of_problem, const double* x, const double* y, int64_t B,
+                                     int32_t N, double* lml, double* grad, int32_t* status, int32_t mem) {
+  if (!window_of_problem) return ctx ? fail(ctx, CNGP_ERR_INVALID, "lml_grad_windows: window_of_problem is null") : CNGP_ERR_INVALID;
+  return cngp_lml_grad_impl(ctx, kernel, theta, n_problems, x, y, B, N, lml, grad, status, mem, window_of_problem);
 }
 
 // ------------------------------------------------------------------------------------------------------------

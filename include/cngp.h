@@ -7,6 +7,8 @@
  *                               core_navigation/script/gp_slip_node.py:35,47-50 (rows a3, a6), for B windows at once
  *   cngp_lml_grad_batch         replaces the objective/gradient evaluation inside m.optimize(),
  *                               gp_slip_node.py:36 (rows a3, a4), for C hyper-parameter candidates x B windows
+ *   cngp_lml_grad_windows       the same objective with one hyper-parameter vector per window (the evaluation each
+ *                               L-BFGS-B iteration of B concurrent m.optimize() calls makes)
  *   cngp_optimize_batch         replaces m.optimize() itself (gp_slip_node.py:36; paramz L-BFGS-B on softplus hypers)
  *   cngp_gp_slip_batch          replaces the whole callback gp_slip_node.py:16-63 (rows a1-a7): train split,
  *                               prediction grid, predict, mean[n:], sigma = 2 sqrt(var[n:])
@@ -131,6 +133,14 @@ int cngp_predict_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* t
 int cngp_lml_grad_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t C,
                         const double* x, const double* y, int64_t B, int32_t N,
                         double* lml, double* grad, int32_t* status, int32_t mem);
+
+/* The same objective for n_problems independent (hyper-parameter vector, window) pairs: problem p evaluates theta
+ * row p [n_problems][P] on window window_of_problem[p] of the B windows.  This is what every iteration of a batch of
+ * independent m.optimize() runs needs (gp_slip_node.py:36): each window is at its own theta, and windows that have
+ * converged drop out of the list.  lml [n_problems]; grad [n_problems][P] (may be NULL); status [n_problems]. */
+int cngp_lml_grad_windows(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t n_problems,
+                          const int32_t* window_of_problem, const double* x, const double* y, int64_t B, int32_t N,
+                          double* lml, double* grad, int32_t* status, int32_t mem);
 
 /* Batched hyper-parameter fit (row a4): L-BFGS (history 10) on softplus-transformed [theta, noise] from theta0,
  * one independent optimiser per window, objective/gradient on the GPU.  theta0 [B][P] or shared (stride 0);
