@@ -36,9 +36,9 @@ def _sources():
 
 def _newest_dep():
     t = 0.0
-    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include"), os.path.join(HERE, "host")):
         for f in os.listdir(root):
-            if f.endswith((".cu", ".cuh", ".h")):
+            if f.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 t = max(t, os.path.getmtime(os.path.join(root, f)))
     return t
 
@@ -46,6 +46,8 @@ def _newest_dep():
 def build(force: bool = False, verbose: bool = False) -> str:
     units = _sources()
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_dep():
+        if not os.path.exists(HOST_LIB) or os.path.getmtime(HOST_LIB) < os.path.getmtime(LIB):
+            build_host()
         return LIB
     os.makedirs(OBJ, exist_ok=True)
 
@@ -72,7 +74,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
+    build_host()
     return LIB
+
+
+HOST_LIB = os.path.join(HERE, "libgp_predictor_b200.so")
+
+
+def build_host() -> str:
+    """The C++ host side above the C ABI: the ROS-free GpPredictor class (include/gp_predictor_b200.hpp)."""
+    src = os.path.join(HERE, "host", "gp_predictor.cpp")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", HOST_LIB, src, LIB, "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("host library build failed")
+    return HOST_LIB
 
 
 if __name__ == "__main__":

@@ -1,0 +1,102 @@
+// ROS-free C++ drop-in of the reference's stop-predictor node class (row a13 of SURVEY.md section 8).
+//
+// Mirrors gp_predictor/include/gp_predictor/gp_predictor.h:18-62 - same class name, same public method names
+// (GPCallBack, LoadParameters, llh_to_enu) and the same public data members the callback fills (gp_data_, H_, P_pred,
+// STM_, Q_, savePos, xy_errSlip, i, slip_i, gp_arrived_time_, new_gp_data_arrived_, stop_cmd_msg_) - with the three ROS
+// attachments replaced by plain callables:
+//     ros::ServiceClient clt_setStopping_  (gp_predictor.cpp:12,26)  -> StoppingService
+//     ros::Publisher     stop_cmd_pub_     (gp_predictor.cpp:13,118) -> StopPublisher
+//     ros::Time::now().toSec()             (gp_predictor.cpp:22,107) -> Clock
+// and the message types by PODs of the same names and fields (core_navigation/msg/GP_Input.msg, GP_Output.msg,
+// srv/SetStopping.srv).  All arithmetic of the callback (gp_predictor.cpp:64-124) runs in the CUDA look-ahead kernel
+// behind cngp_zupt_lookahead_batch; this class only unpacks the service response the way the reference does
+// (row-major 15x15, the H aliasing index of gp_predictor.cpp:38-42 is applied inside the kernel) and turns the kernel's
+// (triggered, i) into the stop command (gp_predictor.cpp:102-122).
+#ifndef GP_PREDICTOR_B200_HPP_
+#define GP_PREDICTOR_B200_HPP_
+
+#include <algorithm>
+#include <array>
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "cngp.h"
+
+namespace core_nav {
+struct Header {
+  uint32_t seq = 0;
+  double stamp = 0.0;
+  std::string frame_id;
+};
+struct GP_Input {   // core_navigation/msg/GP_Input.msg:1-3
+  Header header;
+  std::vector<double> time_array, slip_array;
+};
+struct GP_Output {  // core_navigation/msg/GP_Output.msg:1-3
+  Header header;
+  std::vector<double> mean, sigma;
+};
+struct Point {
+  double x = 0, y = 0, z = 0;
+};
+struct SetStopping {  // core_navigation/srv/SetStopping.srv:1-7
+  struct Request { bool stopping = false; } request;
+  struct Response {
+    std::array<double, 225> PvecData{}, QvecData{}, STMvecData{};
+    std::array<double, 60> HvecData{};
+    Point PosData;
+  } response;
+};
+}  // namespace core_nav
+
+namespace std_msgs {
+struct Float64 { double data = 0.0; };
+}
+
+class GpPredictor {
+ public:
+  typedef std::array<double, 3> Vector3;
+  using StoppingService = std::function<bool(core_nav::SetStopping&)>;
+  using StopPublisher = std::function<void(const std_msgs::Float64&)>;
+  using Clock = std::function<double()>;
+
+  // ctx: a cngp context owned by the caller (one per GPU).
+  GpPredictor(cngp_ctx* ctx, StoppingService stopping_service, StopPublisher stop_cmd_pub, Clock now);
+
+  // gp_predictor.cpp:17-132.  Returns true when a stop command was published.
+  bool GPCallBack(const core_nav::GP_Output& gp_data_in_);
+  // Many predictions against the same service response (Monte-Carlo, configs[3]): mean/sigma [B][M] row-major.
+  // triggered/i_stop [B]; nothing is published.
+  int GPCallBackBatch(const double* mean, const double* sigma, int64_t B, int32_t M, int32_t* triggered, int32_t* i_stop,
+                      double* xy_err);
+  // gp_predictor.cpp:134-142: init_llh/{x,y,z}, init_ecef/{x,y,z}.  The reference never calls it;
+  // without it the defaults of core_navigation/config/init_params.yaml:9-16 apply.
+  bool LoadParameters(const std::map<std::string, double>& params);
+  // gp_predictor.cpp:144-178 (evaluated on the device)
+  Vector3 llh_to_enu(const double latitude, const double longitude, const double height);
+
+  core_nav::GP_Output gp_data_;
+  std::array<double, 60> H_{};        // as received: HvecData (the kernel applies the reference's index)
+  std::array<double, 225> P_pred{}, STM_{}, Q_{};
+  Vector3 savePos{};
+  std_msgs::Float64 stop_cmd_msg_;
+  bool new_gp_data_arrived_ = false;
+  double gp_arrived_time_ = 0.0;
+  double xy_errSlip = 0.0;
+  double init_ecef_x, init_ecef_y, init_ecef_z, init_x, init_y, init_z;
+  int slip_i = 0;
+  int i = 0;
+  cngp_stop_config stop_config;       // every hard-coded constant of gp_predictor.cpp:73-88,102 (defaults = reference)
+
+ private:
+  cngp_ctx* ctx_;
+  StoppingService clt_setStopping_;
+  StopPublisher stop_cmd_pub_;
+  Clock now_;
+  void sync_init();
+};
+
+#endif  // GP_PREDICTOR_B200_HPP_

@@ -110,3 +110,17 @@ def test_gp_slip_rejects_ragged_spans(gp_ctx):
     x[1] *= 1.5
     with pytest.raises(CngpError):
         gp_ctx.gp_slip("rbf", x, y, theta=syn.theta_for("rbf"))
+
+
+def test_python_node_mirror(slipval):
+    """corenav_gp_b200.gp_slip_node keeps the reference script's surface: callback(data) publishes a GP_Output."""
+    from corenav_gp_b200 import gp_slip_node as node
+    t, s = slipval
+    got = []
+    node.pub.sink = got.append
+    th = np.array([0.5, 6.0, 0.01, 2e-3])
+    msg = node.callback(node.GP_Input(time_array=t.tolist(), slip_array=s.tolist()), theta=th)
+    node.pub.sink = None
+    mu, sg = go.gp_slip_callback(t, s, go.KernelExpr("rbf*brownian"), theta=th[:-1], noise=th[-1])
+    assert got and got[0] is msg and node.pub.last is msg
+    assert rel(msg.mean, mu) < TOL and rel(msg.sigma, sg) < TOL
