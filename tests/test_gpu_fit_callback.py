@@ -76,7 +76,7 @@ def test_gp_slip_callback_fixed_theta_matches_oracle(gp_ctx, slipval):
     mean, sigma, status = gp_ctx.gp_slip("rbf*brownian", t[None], s[None], theta=th)
     mu, sg = go.gp_slip_callback(t, s, go.KernelExpr("rbf*brownian"), theta=th[:-1], noise=th[-1])
     assert status[0] == 0 and mean.shape == (1, mu.size)
-    assert mu.size == 620                     # ceil(46.0 + 600 - 26.2) - 199 grid points are published
+    assert mu.size == 421                     # grid = ceil(46.0 + 600 - 26.2) = 620 points, entries [199:] are published
     assert rel(mean[0], mu) < TOL and rel(sigma[0], sg) < TOL
 
 
