@@ -32,6 +32,14 @@ class StopConfig(C.Structure):
                 ("init_llh", C.c_double * 3), ("init_ecef", C.c_double * 3)]
 
 
+class LargePlan(C.Structure):
+    _fields_ = [("N", c_i64), ("n_pad", c_i64), ("world", c_i32), ("rank", c_i32), ("row_tiles", c_i64),
+                ("n_blockcols", c_i64), ("n_local_blockcols", c_i64), ("local_doubles", c_i64),
+                ("panel_doubles", c_i64), ("winv_doubles", c_i64)]
+
+
+LARGE_NB = 256
+
 # every symbol include/cngp.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "cngp_version": (C.c_int, []),
@@ -61,6 +69,13 @@ SIGNATURES = {
                                             C.POINTER(StopConfig), c_ip, c_ip, c_ip, c_dp, c_i32]),
     "cngp_llh_to_enu": (C.c_int, [c_vp, c_dp, c_i64, C.POINTER(StopConfig), c_dp, c_i32]),
     "cngp_chol_large": (C.c_int, [c_vp, C.POINTER(Kernel), c_dp, c_dp, c_dp, c_i64, c_dp, c_dp, c_dp, c_dp, c_i32]),
+    "cngp_large_make_plan": (C.c_int, [c_i64, c_i32, c_i32, C.POINTER(LargePlan)]),
+    "cngp_large_assemble": (C.c_int, [c_vp, C.POINTER(LargePlan), C.POINTER(Kernel), c_dp, c_dp, c_dp, c_dp]),
+    "cngp_large_factor_panel": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_dp, c_dp, c_ip]),
+    "cngp_large_update": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_i64, c_i64]),
+    "cngp_large_reduce": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_dp, c_ip, c_dp, c_dp]),
+    "cngp_large_backsolve_step": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_dp, c_i64, c_dp, c_dp]),
+    "cngp_large_matvec": (C.c_int, [c_vp, C.POINTER(Kernel), c_dp, c_dp, c_dp, c_i64, c_dp]),
 }
 
 _lib = None

@@ -279,26 +279,37 @@ class GpContext:
         return enu
 
     def chol_large(self, kernel, theta, x, y, want_alpha: bool = False):
-        """Single large window (N up to 32768+): returns dict(logdet, quad, lml[, alpha])."""
+        """Single large window (BASELINE.json configs[4], N = 32768) on this GPU: blocked FP64 Cholesky in HBM.
+        theta: host [P]; x, y: host arrays or CUDA tensors [N].  Returns dict(logdet, quad, lml[, alpha]).
+        Raises CngpError when the matrix is not positive definite (rc = failing pivot)."""
         k = parse_kernel(kernel)
         dev = _is_cuda(x)
         N = int(np.prod(tuple(x.shape)))
-        outs = self._empty((3,), np.float64, False)
+        th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))
+        if th.size != k.n_params + 1:
+            raise CngpError(f"theta has {th.size} entries, kernel needs {k.n_params + 1} (noise last)")
+        outs = np.empty(3)
         alpha = self._empty((N,), np.float64, dev) if want_alpha else None
-        a = [_Arg(theta, np.float64, dev), _Arg(x, np.float64, dev), _Arg(y, np.float64, dev),
-             _Arg(alpha, np.float64, dev, True)]
+        a = [_Arg(x, np.float64, dev), _Arg(y, np.float64, dev), _Arg(alpha, np.float64, dev, True)]
         self._bind_stream(dev)
-        if dev:
-            o = torch.empty(3, dtype=torch.float64, device=f"cuda:{self.device}")
-            rc = self.lib.cngp_chol_large(self.h, C.byref(k), a[0].ptr, a[1].ptr, a[2].ptr, N, o.data_ptr(),
-                                          o.data_ptr() + 8, o.data_ptr() + 16, a[3].ptr, L.MEM_DEVICE)
-            self._check(rc, "cngp_chol_large")
-            outs = o.cpu().numpy()
-        else:
-            rc = self.lib.cngp_chol_large(self.h, C.byref(k), a[0].ptr, a[1].ptr, a[2].ptr, N, outs.ctypes.data,
-                                          outs.ctypes.data + 8, outs.ctypes.data + 16, a[3].ptr, L.MEM_HOST)
-            self._check(rc, "cngp_chol_large")
+        rc = self.lib.cngp_chol_large(self.h, C.byref(k), th.ctypes.data, a[0].ptr, a[1].ptr, N, outs.ctypes.data,
+                                      outs.ctypes.data + 8, outs.ctypes.data + 16, a[2].ptr,
+                                      L.MEM_DEVICE if dev else L.MEM_HOST)
+        if rc > 0:
+            raise CngpError(f"cngp_chol_large: matrix not positive definite at pivot {rc}")
+        self._check(rc, "cngp_chol_large")
         res = dict(logdet=float(outs[0]), quad=float(outs[1]), lml=float(outs[2]))
         if want_alpha:
             res["alpha"] = alpha
         return res
+
+    def large_matvec(self, kernel, theta, x, v):
+        """r = (K(x,x) + (noise + 1e-8) I) v evaluated on the fly on the device; x, v CUDA tensors [N]."""
+        k = parse_kernel(kernel)
+        th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))
+        N = int(x.numel())
+        r = torch.empty(N, dtype=torch.float64, device=x.device)
+        self._bind_stream(True)
+        rc = self.lib.cngp_large_matvec(self.h, C.byref(k), th.ctypes.data, x.data_ptr(), v.data_ptr(), N, r.data_ptr())
+        self._check(rc, "cngp_large_matvec")
+        return r

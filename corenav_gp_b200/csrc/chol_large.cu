@@ -1,4 +1,690 @@
-// placeholder - replaced below in this round
-#include "../../include/cngp.h"
-extern "C" int cngp_chol_large(cngp_ctx*, const cngp_kernel*, const double*, const double*, const double*, int64_t,
-                               double*, double*, double*, double*, int32_t) { return CNGP_ERR_UNSUPPORTED; }
+// Large single-window exact GP (BASELINE.json configs[4], N = 32768): blocked right-looking FP64 Cholesky in HBM.
+//
+// Same inference as gp_fit.cuh (row a3: GPy ExactGaussianInference reached from GPRegression(...) at
+// core_navigation/script/gp_slip_node.py:35 - Ky = K + (sigma_n^2 + 1e-8) I, dpotrf, dpotrs, logdet, LML) for a window
+// that does not fit one SM.  Nothing in the reference runs at this size; the algorithm is the textbook blocked
+// factorisation, organised for B200:
+//
+//  * storage: 8x8 FP64 tiles (the lane layout of cngp_common.cuh), column-tile-major: tile (rt, ct) at
+//    A[(ct * row_tiles + rt) * 64].  For a fixed column tile the row tiles are contiguous, so a 16-tile operand slab
+//    is ONE 8 KB bulk-TMA copy, and a warp reads/writes a C tile as one 512 B coalesced access.
+//  * block columns of NB = 256 columns, dealt cyclically over `world` GPUs (1-D block-cyclic); y is carried as one
+//    extra row tile under the matrix so z = L^-1 y falls out of the factorisation (as in gp_fit_kernel).
+//  * per block column k (owner only): the 256x256 diagonal block is factored by gp_fit_kernel<KID_TILES> (the same
+//    in-shared-memory tile Cholesky as the batched windows), inverted tile-wise (large_trinv_kernel), and the panel
+//    below is formed as a product with the inverse - a GEMM, not a substitution.
+//  * trailing update C -= P P^T (large_gemm_kernel, mode 1): the only dense contraction, N^3/3 flop.  128x128 C tiles
+//    per CTA, 8 consumer warps x 32 accumulator tiles in registers (mma.sync m8n8k4 f64 - FP64 has no tcgen05 kind),
+//    operands streamed through a 4-stage shared-memory ring by a producer warp issuing cp.async.bulk (UBLKCP) with
+//    mbarrier completion; C is loaded straight into the accumulators before the main loop and stored once.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <type_traits>
+#include <vector>
+
+#include "cngp_internal.h"
+#include "gp_fit.cuh"
+
+using namespace cngp;
+
+namespace {
+
+constexpr int LG_NB = CNGP_LARGE_NB;     // columns per block column
+constexpr int LG_BT = LG_NB / 8;         // 32 tiles
+constexpr int LG_BLK = 16;               // CTA tile edge in tiles (128 rows / columns)
+constexpr int LG_KC = 2;                 // k-tiles per pipeline stage
+constexpr int LG_STAGES = 4;
+constexpr int LG_CONSUMERS = 8;
+constexpr int LG_THREADS = LG_CONSUMERS * 32;
+constexpr int LG_SLAB = LG_BLK * 64;     // doubles in a 16-tile slab (8 KB)
+constexpr int LG_STAGE_DOUBLES = 2 * LG_KC * LG_SLAB;
+constexpr size_t LG_SMEM = (size_t)LG_STAGES * LG_STAGE_DOUBLES * 8;
+
+// ------------------------------------------------------------------------------------------------------------
+// assembly
+// ------------------------------------------------------------------------------------------------------------
+struct AsmArgs {
+  KProg kp;
+  const double* theta;   // device [P]
+  const double* x;       // device [N]
+  const double* y;       // device [N]
+  long long N, n_pad;
+  long long row_tiles;
+  int world, rank;
+  double* A;
+};
+
+constexpr int ASM_WARPS = 8;
+constexpr int ASM_TILES_PER_WARP = 8;
+
+// grid (ceil(row_tiles / 64), local column tiles); each warp writes 8 consecutive row tiles of one column tile
+template <int KID>
+__global__ void __launch_bounds__(ASM_WARPS * 32) large_assemble_kernel(const AsmArgs a) {
+  __shared__ LeafConst hc[CNGP_MAX_LEAVES];
+  __shared__ KProg kps;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
+  const long long lct = blockIdx.y;
+  const long long c = (lct / LG_BT) * a.world + a.rank;          // global block column
+  const long long gct = c * LG_BT + lct % LG_BT;                 // global column tile
+  const long long NT = a.n_pad / 8;
+  FastK<KID> fk;
+  if (KID == KID_GENERIC) {
+    if (threadIdx.x < a.kp.n_leaves)
+      hc[threadIdx.x] = leaf_prepare(a.kp.leaf_type[threadIdx.x], a.theta + a.kp.leaf_param[threadIdx.x]);
+    if (threadIdx.x == 0) kps = a.kp;
+    __syncthreads();
+  } else {
+    fk.init(a.theta);
+  }
+  const double dadd = a.theta[a.kp.n_params] + CNGP_JITTER;
+  const long long c0 = 8 * gct + 2 * q, c1 = c0 + 1;
+  const double xc0 = c0 < a.N ? a.x[c0] : 0.0, xc1 = c1 < a.N ? a.x[c1] : 0.0;
+  PointFeat f0{xc0, 0.0, 0.0, 0.0}, f1{xc1, 0.0, 0.0, 0.0};
+  if (KID != KID_GENERIC) { f0 = fk.point(xc0); f1 = fk.point(xc1); }
+  const long long first_rt = (gct / LG_BLK) * LG_BLK;            // whole diagonal 16x16 tile blocks are filled
+  double* col = a.A + lct * a.row_tiles * 64;
+  for (int t = 0; t < ASM_TILES_PER_WARP; ++t) {
+    const long long rt = ((long long)blockIdx.x * ASM_WARPS + w) * ASM_TILES_PER_WARP + t;
+    if (rt >= a.row_tiles || rt < first_rt) continue;            // storage is zero-filled beforehand
+    tile2 v{0.0, 0.0};
+    if (rt < NT) {
+      const long long row = 8 * rt + r;
+      if (row < a.N) {
+        const double xr = a.x[row];
+        if (KID == KID_GENERIC) {
+          if (c0 < a.N) v.a = keval_generic_sym(&kps, hc, xr, xc0, row == c0);
+          if (c1 < a.N) v.b = keval_generic_sym(&kps, hc, xr, xc1, row == c1);
+        } else {
+          const PointFeat fr = fk.point(xr);
+          if (c0 < a.N) v.a = fk.eval(fr, f0, row == c0);
+          if (c1 < a.N) v.b = fk.eval(fr, f1, row == c1);
+        }
+        if (row == c0) v.a += dadd;
+        if (row == c1) v.b += dadd;
+      } else {
+        if (row == c0) v.a = 1.0;                                // identity padding
+        if (row == c1) v.b = 1.0;
+      }
+    } else if (rt == NT) {
+      if (r == 0) { v.a = c0 < a.N ? a.y[c0] : 0.0; v.b = c1 < a.N ? a.y[c1] : 0.0; }
+    }
+    tile_store(col + rt * 64, lane, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// inverse of the factored diagonal block: W = L^-1 as 32 x 32 tiles in [k-tile][row-tile] order (the Y operand
+// layout of large_gemm_kernel), from the packed factor gp_fit_kernel writes (diagonal tiles already inverted).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TRI_WARPS = 16;
+__device__ __forceinline__ tile2 tile_load_transposed(const double* tile, int lane) {
+  const int r = lane >> 2, q = lane & 3;
+  return tile2{tile[(2 * q) * 8 + r], tile[(2 * q + 1) * 8 + r]};
+}
+
+__global__ void __launch_bounds__(TRI_WARPS * 32) large_trinv_kernel(const double* Lp, double* WT, double* W) {
+  const int nt = LG_BT;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // WT(i,j) = (L^-1)_ij^T, column by column:  T^T = sum_{k=j}^{i-1} WT(k,j) L(i,k)^T,  WT(i,j) = -T^T inv(L_ii)^T
+  // heavy columns (small j) are paired with light ones on the same warp: columns w and 31 - w
+  for (int pass = 0; pass < 2; ++pass) {
+    const int j = pass == 0 ? w : nt - 1 - w;
+    tile_store(WT + (long long)tile_index(j, j, nt) * 64, lane,
+               tile_load_transposed(Lp + (long long)tile_index(j, j, nt) * 64, lane));
+    __syncwarp();
+    for (int i = j + 1; i < nt; ++i) {
+      tile2 T0{0.0, 0.0}, T1{0.0, 0.0};
+      int k = j;
+      for (; k + 1 < i; k += 2) {
+        tile_mma(T0, tile_load(WT + (long long)tile_index(k, j, nt) * 64, lane),
+                 tile_load(Lp + (long long)tile_index(i, k, nt) * 64, lane));
+        tile_mma(T1, tile_load(WT + (long long)tile_index(k + 1, j, nt) * 64, lane),
+                 tile_load(Lp + (long long)tile_index(i, k + 1, nt) * 64, lane));
+      }
+      if (k < i)
+        tile_mma(T0, tile_load(WT + (long long)tile_index(k, j, nt) * 64, lane),
+                 tile_load(Lp + (long long)tile_index(i, k, nt) * 64, lane));
+      const tile2 nT{-(T0.a + T1.a), -(T0.b + T1.b)};
+      tile2 Wt{0.0, 0.0};
+      tile_mma(Wt, nT, tile_load(Lp + (long long)tile_index(i, i, nt) * 64, lane));
+      tile_store(WT + (long long)tile_index(i, j, nt) * 64, lane, Wt);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // W tile (row tile i, k-tile j) = WT(i,j)^T at W[(j * 32 + i) * 64]; zero above the diagonal
+  for (int idx = w; idx < nt * nt; idx += TRI_WARPS) {
+    const int j = idx / nt, i = idx % nt;
+    tile2 v{0.0, 0.0};
+    if (i >= j) v = tile_load_transposed(WT + (long long)tile_index(i, j, nt) * 64, lane);
+    tile_store(W + (long long)idx * 64, lane, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// tile GEMM:  C(rt, ct) (-)= sum_k X(k, rt) Y(k, n)^T
+// ------------------------------------------------------------------------------------------------------------
+struct GemmArgs {
+  const double* X; long long x_kstride;   // X tile (k, rt) at X + k * x_kstride + rt * 64
+  const double* Y; long long y_kstride;   // Y tile (k, n)  at Y + k * y_kstride + n * 64
+  double* C;       long long c_cstride;   // C tile (rt, ct) at C + ct * c_cstride + rt * 64
+  int mode;       // 0: C = X Y^T, Y lower-triangular inverse block (k-tiles up to the column block's last tile)
+                  // 1: C -= X Y^T over all 32 k-tiles; column blocks are local block-cyclic, lower blocks only
+  int rb0;        // first row block of the launch (units of 16 tiles); blockIdx.x counts from it
+  int lcb0;       // mode 1: first local column block (units of 16 tiles); blockIdx.y counts from it
+  int world, rank;
+};
+
+__global__ void __launch_bounds__(LG_THREADS, 1) large_gemm_kernel(const GemmArgs a) {
+  extern __shared__ __align__(128) double ring[];
+  __shared__ unsigned long long bars[2 * LG_STAGES];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const long long rt0 = (long long)(a.rb0 + blockIdx.x) * LG_BLK;
+  long long n0, ct0;
+  int KT;
+  if (a.mode == 0) {
+    n0 = ct0 = (long long)blockIdx.y * LG_BLK;
+    KT = ((int)blockIdx.y + 1) * LG_BLK;
+  } else {
+    const long long lct0 = (long long)(a.lcb0 + blockIdx.y) * LG_BLK;
+    const long long c = (lct0 / LG_BT) * a.world + a.rank;
+    n0 = c * LG_BT + lct0 % LG_BT;       // panel rows that face this column block
+    ct0 = lct0;
+    KT = LG_BT;
+    if (rt0 < n0) return;                // block strictly above the diagonal
+  }
+  const uint32_t full_u32 = smem_u32(&bars[0]), empty_u32 = smem_u32(&bars[LG_STAGES]);
+  if (tid == 0) {
+    for (int s = 0; s < LG_STAGES; ++s) { mbar_init(full_u32 + 8 * s, 1); mbar_init(empty_u32 + 8 * s, LG_CONSUMERS); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int n_it = KT / LG_KC;
+  const uint32_t ring_u32 = smem_u32(ring);
+  // one lane streams the operand slabs of iteration `it`: LG_KC k-tiles of X and of Y into slot it % LG_STAGES
+  auto issue = [&](int it) {
+    const int s = it % LG_STAGES;
+    mbar_expect_tx(full_u32 + 8 * s, LG_STAGE_DOUBLES * 8);
+    const uint32_t dst = ring_u32 + s * LG_STAGE_DOUBLES * 8;
+#pragma unroll
+    for (int kk = 0; kk < LG_KC; ++kk) {
+      const long long k = (long long)it * LG_KC + kk;
+      bulk_g2s(dst + kk * LG_SLAB * 8, a.X + k * a.x_kstride + rt0 * 64, LG_SLAB * 8, full_u32 + 8 * s);
+      bulk_g2s(dst + (LG_KC + kk) * LG_SLAB * 8, a.Y + k * a.y_kstride + n0 * 64, LG_SLAB * 8, full_u32 + 8 * s);
+    }
+  };
+  if (tid == 0)
+    for (int it = 0; it < LG_STAGES - 1 && it < n_it; ++it) issue(it);
+
+  // ---- consumers: warp (wr, wc) owns row tiles wr*8 .. +8 and column tiles wc*4 .. +4 of the block ----
+  const int wr = w >> 2, wc = w & 3;
+  tile2 acc[8][4];
+  double* cbase = a.C + (ct0 + wc * 4) * a.c_cstride + (rt0 + wr * 8) * 64 + 2 * lane;
+  if (a.mode == 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double2 v = *reinterpret_cast<const double2*>(cbase + j * a.c_cstride + i * 64);
+        acc[i][j] = tile2{v.x, v.y};
+      }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i][j] = tile2{0.0, 0.0};
+  }
+  const bool neg = a.mode == 1;
+  for (int it = 0; it < n_it; ++it) {
+    const int s = it % LG_STAGES;
+    // refill duty rotates over the warps: the slot consumed at iteration it-1 gets iteration it + LG_STAGES - 1
+    if (w == (it % LG_CONSUMERS) && lane == 0 && it + LG_STAGES - 1 < n_it) {
+      if (it >= 1) mbar_wait(empty_u32 + 8 * ((it - 1) % LG_STAGES), (uint32_t)((it - 1) / LG_STAGES) & 1u);
+      issue(it + LG_STAGES - 1);
+    }
+    __syncwarp();
+    mbar_wait(full_u32 + 8 * s, (uint32_t)(it / LG_STAGES) & 1u);
+    const double* xs = ring + s * LG_STAGE_DOUBLES + wr * 8 * 64 + 2 * lane;
+    const double* ys = ring + s * LG_STAGE_DOUBLES + LG_KC * LG_SLAB + wc * 4 * 64 + 2 * lane;
+#pragma unroll
+    for (int kk = 0; kk < LG_KC; ++kk) {
+      tile2 Yf[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double2 v = *reinterpret_cast<const double2*>(ys + kk * LG_SLAB + j * 64);
+        Yf[j] = tile2{v.x, v.y};
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double2 v = *reinterpret_cast<const double2*>(xs + kk * LG_SLAB + i * 64);
+        const tile2 Xf = neg ? tile2{-v.x, -v.y} : tile2{v.x, v.y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tile_mma(acc[i][j], Xf, Yf[j]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_u32 + 8 * s);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<double2*>(cbase + j * a.c_cstride + i * 64) = make_double2(acc[i][j].a, acc[i][j].b);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// z gather / reductions / back substitution / matvec
+// ------------------------------------------------------------------------------------------------------------
+// z[8 gct + c] = row 0 of tile (n_pad/8, lct); sums[0] = sum logdet of local blocks, sums[1] = sum z^2,
+// sums[2] = first failing pivot (global, 1-based) or 0.  One CTA.
+__global__ void __launch_bounds__(1024) large_reduce_kernel(const double* A, long long row_tiles, long long NT,
+                                                            long long n_local_ct, int world, int rank,
+                                                            const double* logdet, const int* status,
+                                                            long long n_blockcols, double* z, double* sums) {
+  __shared__ double red[32];
+  double qs = 0.0;
+  for (long long i = threadIdx.x; i < n_local_ct * 8; i += blockDim.x) {
+    const long long lct = i / 8, cc = i % 8;
+    const long long c = (lct / LG_BT) * world + rank;
+    const long long gct = c * LG_BT + lct % LG_BT;
+    const double v = A[(lct * row_tiles + NT) * 64 + cc];
+    z[8 * gct + cc] = v;
+    qs += v * v;
+  }
+  for (int o = 16; o; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = qs;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ld = 0.0, fp = 0.0;
+    for (long long k = rank; k < n_blockcols; k += world) {
+      ld += logdet[k];
+      if (status[k] < 0 && fp == 0.0) fp = (double)(k * LG_NB - status[k]);
+    }
+    double q2 = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) q2 += red[i];
+    sums[0] = ld; sums[1] = q2; sums[2] = fp;
+  }
+}
+
+// partial[chunk][c] = sum over this chunk's row tiles (below the diagonal block) of L(row, c) alpha(row)
+constexpr int BACK_CHUNKS = 32;
+__global__ void __launch_bounds__(256) large_back_partial_kernel(const double* Acol /* block column base */,
+                                                                 long long row_tiles, long long rt_first, long long NT,
+                                                                 const double* alpha, double* partial) {
+  __shared__ double red[8][8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
+  const int kt = blockIdx.x, chunk = blockIdx.y;
+  const long long n_rt = NT - rt_first;
+  const long long per = (n_rt + BACK_CHUNKS - 1) / BACK_CHUNKS;
+  const long long lo = rt_first + chunk * per, hi = min(NT, lo + per);
+  double s0 = 0.0, s1 = 0.0;
+  for (long long rt = lo + w; rt < hi; rt += 8) {
+    const double2 v = *reinterpret_cast<const double2*>(Acol + ((long long)kt * row_tiles + rt) * 64 + 2 * lane);
+    const double al = alpha[8 * rt + r];
+    s0 = fma(v.x, al, s0);
+    s1 = fma(v.y, al, s1);
+  }
+  for (int o = 4; o < 32; o <<= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if (r == 0) { red[w][2 * q] = s0; red[w][2 * q + 1] = s1; }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    partial[chunk * LG_NB + kt * 8 + threadIdx.x] = s;
+  }
+}
+
+// alpha_j = inv(L_jj)^T (z_j - sum_chunks partial)
+__global__ void __launch_bounds__(LG_NB) large_back_finish_kernel(const double* W, const double* zj, const double* partial,
+                                                                  double* alpha_j) {
+  __shared__ double t[LG_NB];
+  const int c = threadIdx.x;
+  double s = zj[c];
+  for (int ch = 0; ch < BACK_CHUNKS; ++ch) s -= partial[ch * LG_NB + c];
+  t[c] = s;
+  __syncthreads();
+  // alpha[c] = sum_row W[row][c] t[row];  W element (row, c) is in tile (k-tile c/8, row tile row/8)
+  const double* wt = W + (long long)(c / 8) * LG_BT * 64 + (c % 8);
+  double acc = 0.0;
+  for (int row = c - (c % 8); row < LG_NB; ++row) acc = fma(wt[(row / 8) * 64 + (row % 8) * 8], t[row], acc);
+  alpha_j[c] = acc;
+}
+
+// r = Ky v with Ky evaluated on the fly; one warp per row
+template <int KID>
+__global__ void __launch_bounds__(256) large_matvec_kernel(KProg kp, const double* theta, const double* x,
+                                                           const double* v, long long N, double* out) {
+  __shared__ LeafConst hc[CNGP_MAX_LEAVES];
+  __shared__ KProg kps;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  FastK<KID> fk;
+  if (KID == KID_GENERIC) {
+    if (threadIdx.x < kp.n_leaves) hc[threadIdx.x] = leaf_prepare(kp.leaf_type[threadIdx.x], theta + kp.leaf_param[threadIdx.x]);
+    if (threadIdx.x == 0) kps = kp;
+    __syncthreads();
+  } else {
+    fk.init(theta);
+  }
+  const long long row = (long long)blockIdx.x * 8 + w;
+  if (row >= N) return;
+  const double xr = x[row];
+  PointFeat fr{xr, 0.0, 0.0, 0.0};
+  if (KID != KID_GENERIC) fr = fk.point(xr);
+  double s = 0.0;
+  for (long long c = lane; c < N; c += 32) {
+    const double xc = x[c];
+    double k;
+    if (KID == KID_GENERIC) k = keval_generic_sym(&kps, hc, xr, xc, row == c);
+    else k = fk.eval(fr, fk.point(xc), row == c);
+    if (row == c) k += theta[kp.n_params] + CNGP_JITTER;
+    s = fma(k, v[c], s);
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = s;
+}
+
+template <typename F>
+void dispatch_kid(int kid, F&& f) {
+  switch (kid) {
+    case KID_RBF: f(std::integral_constant<int, KID_RBF>()); break;
+    case KID_RBF_PER: f(std::integral_constant<int, KID_RBF_PER>()); break;
+    case KID_RBF_BROWN: f(std::integral_constant<int, KID_RBF_BROWN>()); break;
+    default: f(std::integral_constant<int, KID_GENERIC>()); break;
+  }
+}
+
+int cuda_fail(cngp_ctx* ctx, const char* what, cudaError_t e) {
+  char tmp[256];
+  snprintf(tmp, sizeof tmp, "%s: %s", what, cudaGetErrorString(e));
+  return cngp_set_error(ctx, CNGP_ERR_CUDA, tmp);
+}
+#define LCU(ctx, call)                                        \
+  do {                                                        \
+    cudaError_t e_ = (call);                                  \
+    if (e_ != cudaSuccess) return cuda_fail(ctx, #call, e_);  \
+  } while (0)
+
+// scratch slots of the context used here
+enum { SLOT_THETA = 20, SLOT_LPACK = 21, SLOT_WT = 22, SLOT_Z33 = 23, SLOT_PARTIAL = 24 };
+
+inline long long local_index_of(long long c_lo, int world, int rank) {   // smallest l with l*world + rank >= c_lo
+  if (c_lo <= rank) return 0;
+  return (c_lo - rank + world - 1) / world;
+}
+
+}  // namespace
+
+extern "C" int cngp_large_make_plan(int64_t N, int32_t world, int32_t rank, cngp_large_plan* p) {
+  if (!p || N <= 0 || world <= 0 || rank < 0 || rank >= world) return CNGP_ERR_INVALID;
+  memset(p, 0, sizeof *p);
+  p->N = N;
+  p->n_pad = (N + LG_NB - 1) / LG_NB * LG_NB;
+  p->world = world;
+  p->rank = rank;
+  p->row_tiles = p->n_pad / 8 + LG_BLK;
+  p->n_blockcols = p->n_pad / LG_NB;
+  p->n_local_blockcols = p->n_blockcols > rank ? (p->n_blockcols - rank + world - 1) / world : 0;
+  p->local_doubles = p->n_local_blockcols * LG_BT * p->row_tiles * 64;
+  p->panel_doubles = (int64_t)LG_BT * p->row_tiles * 64;
+  p->winv_doubles = p->n_local_blockcols * LG_BT * LG_BT * 64;
+  return CNGP_OK;
+}
+
+extern "C" int cngp_large_assemble(cngp_ctx* ctx, const cngp_large_plan* p, const cngp_kernel* kernel, const double* theta,
+                                   const double* x, const double* y, double* A) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!p || !kernel || !theta || !x || !y || !A) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_assemble: bad argument");
+  KProg kp;
+  int rc = cngp_build_kprog(kernel, &kp);
+  if (rc) return cngp_set_error(ctx, rc, "large_assemble: invalid kernel expression");
+  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
+  cudaStream_t s = cngp_ctx_stream(ctx);
+  const int P = kp.n_params + 1;
+  double* d_theta = (double*)cngp_ctx_buf(ctx, SLOT_THETA, sizeof(double) * (CNGP_MAX_PARAMS + 1));
+  if (!d_theta) return cngp_set_error(ctx, CNGP_ERR_NOMEM, "large_assemble: theta buffer");
+  LCU(ctx, cudaMemcpyAsync(d_theta, theta, sizeof(double) * P, cudaMemcpyHostToDevice, s));
+  LCU(ctx, cudaStreamSynchronize(s));   // theta is a host stack/array of the caller
+  if (p->n_local_blockcols == 0) return CNGP_OK;
+  LCU(ctx, cudaMemsetAsync(A, 0, sizeof(double) * (size_t)p->local_doubles, s));
+  AsmArgs a;
+  a.kp = kp; a.theta = d_theta; a.x = x; a.y = y; a.N = p->N; a.n_pad = p->n_pad; a.row_tiles = p->row_tiles;
+  a.world = p->world; a.rank = p->rank; a.A = A;
+  const long long n_local_ct = p->n_local_blockcols * LG_BT;
+  const int per_cta = ASM_WARPS * ASM_TILES_PER_WARP;
+  // grid.y is limited to 65535: launch in slices of column tiles
+  for (long long y0 = 0; y0 < n_local_ct; y0 += 32768) {
+    const long long ny = std::min<long long>(32768, n_local_ct - y0);
+    AsmArgs as = a;
+    as.A = A + y0 * p->row_tiles * 64;
+    // the kernel derives the global column from blockIdx.y, so slices must start on a block-column boundary
+    // (32768 is a multiple of 32) and carry their offset through `rank`-relative arithmetic:
+    const long long l0 = y0 / LG_BT;
+    as.rank = (int)(p->rank + l0 * p->world);   // (lct / 32) * world + rank  ==  ((lct + y0) / 32) * world + p->rank
+    dim3 grid((unsigned)((p->row_tiles + per_cta - 1) / per_cta), (unsigned)ny);
+    cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+    dispatch_kid(match_fast_kernel(kp), [&](auto kid) {
+      large_assemble_kernel<decltype(kid)::value><<<grid, ASM_WARPS * 32, 0, s>>>(as);
+    });
+    cngp_ctx_end(ctx);
+  }
+  LCU(ctx, cudaGetLastError());
+  return CNGP_OK;
+}
+
+extern "C" int cngp_large_factor_panel(cngp_ctx* ctx, const cngp_large_plan* p, double* A, int64_t k, double* panel,
+                                       double* winv, double* logdet, int32_t* status) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!p || !A || !panel || !winv || !logdet || !status || k < 0 || k >= p->n_blockcols)
+    return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_factor_panel: bad argument");
+  if (k % p->world != p->rank) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_factor_panel: not the owner of this block column");
+  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
+  cudaStream_t s = cngp_ctx_stream(ctx);
+  const long long l = k / p->world;
+  const long long cstride = p->row_tiles * 64;
+  double* Acol = A + l * LG_BT * cstride;                 // block column k
+  const long long rdiag = k * LG_BT;                      // first row tile of the diagonal block
+  double* Lpack = (double*)cngp_ctx_buf(ctx, SLOT_LPACK, sizeof(double) * tiles_in_lower(LG_BT) * 64);
+  double* WT = (double*)cngp_ctx_buf(ctx, SLOT_WT, sizeof(double) * tiles_in_lower(LG_BT) * 64);
+  double* z33 = (double*)cngp_ctx_buf(ctx, SLOT_Z33, sizeof(double) * (LG_NB + 8));
+  if (!Lpack || !WT || !z33) return cngp_set_error(ctx, CNGP_ERR_NOMEM, "large_factor_panel: scratch");
+  double* Wk = winv + l * LG_BT * LG_BT * 64;
+
+  // 1. diagonal block: tile Cholesky in shared memory (diagonal tiles come out inverted)
+  FitArgs fa;
+  memset(&fa, 0, sizeof fa);
+  fa.theta = nullptr; fa.theta_stride = 0; fa.theta_mode = 0; fa.win_map = nullptr;
+  fa.x = nullptr; fa.y = nullptr; fa.N = LG_NB; fa.nt = LG_BT; fa.n_windows = 1; fa.problem0 = 0;
+  fa.L = Lpack; fa.z = z33; fa.feat = nullptr; fa.lml = nullptr; fa.logdet = logdet + k; fa.quad = nullptr;
+  fa.status = status + k; fa.jitter_retry = 0;
+  fa.Asrc = Acol + rdiag * 64; fa.a_col_stride = cstride;
+  // logdet / status are indexed by the kernel with the problem id p = problem0 + blockIdx.x = 0
+  const size_t smem = fit_smem_bytes(LG_BT);
+  LCU(ctx, cudaFuncSetAttribute(gp_fit_kernel<KID_TILES, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+  gp_fit_kernel<KID_TILES, 16><<<1, 16 * 32, smem, s>>>(fa);
+  cngp_ctx_end(ctx);
+  // 2. inverse of the block factor
+  cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+  large_trinv_kernel<<<1, TRI_WARPS * 32, 0, s>>>(Lpack, WT, Wk);
+  cngp_ctx_end(ctx);
+  // 3. panel = (rows below the diagonal block) inv(L_kk)^T
+  const int RB = (int)(p->row_tiles / LG_BLK);
+  const int rb0 = (int)((rdiag + LG_BT) / LG_BLK);
+  // the panel buffer is compact: tile (k, rt) at panel + (k * (row_tiles - r0) + rt - r0) * 64 with r0 the first row
+  // tile below the diagonal block, so what has to be broadcast is one contiguous prefix of the buffer
+  const long long r0 = rdiag + LG_BT;
+  const long long pstride = (p->row_tiles - r0) * 64;
+  GemmArgs g;
+  g.X = Acol; g.x_kstride = cstride;
+  g.Y = Wk; g.y_kstride = (long long)LG_BT * 64;
+  g.C = panel - r0 * 64; g.c_cstride = pstride;
+  g.mode = 0; g.rb0 = rb0; g.lcb0 = 0; g.world = p->world; g.rank = p->rank;
+  LCU(ctx, cudaFuncSetAttribute(large_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_SMEM));
+  cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+  large_gemm_kernel<<<dim3((unsigned)(RB - rb0), LG_BT / LG_BLK), LG_THREADS, LG_SMEM, s>>>(g);
+  cngp_ctx_end(ctx);
+  // 4. the panel is this block column of L: copy it back under the diagonal block
+  LCU(ctx, cudaMemcpy2DAsync(Acol + r0 * 64, cstride * 8, panel, pstride * 8, (size_t)(p->row_tiles - r0) * 512, LG_BT,
+                             cudaMemcpyDeviceToDevice, s));
+  LCU(ctx, cudaGetLastError());
+  return CNGP_OK;
+}
+
+extern "C" int cngp_large_update(cngp_ctx* ctx, const cngp_large_plan* p, double* A, int64_t k, const double* panel,
+                                 int64_t c_lo, int64_t c_hi) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!p || !A || !panel || k < 0 || k >= p->n_blockcols) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_update: bad argument");
+  c_lo = std::max<int64_t>(c_lo, k + 1);
+  c_hi = std::min<int64_t>(c_hi, p->n_blockcols);
+  if (c_lo >= c_hi) return CNGP_OK;
+  const long long l_lo = local_index_of(c_lo, p->world, p->rank), l_hi = local_index_of(c_hi, p->world, p->rank);
+  if (l_lo >= l_hi) return CNGP_OK;
+  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
+  cudaStream_t s = cngp_ctx_stream(ctx);
+  const long long cstride = p->row_tiles * 64;
+  const int RB = (int)(p->row_tiles / LG_BLK);
+  const long long c_first = l_lo * p->world + p->rank;
+  const int rb0 = (int)(c_first * LG_BT / LG_BLK);
+  const long long r0 = (k + 1) * LG_BT;                     // compact panel layout, see cngp_large_factor_panel
+  const long long pstride = (p->row_tiles - r0) * 64;
+  GemmArgs g;
+  g.X = panel - r0 * 64; g.x_kstride = pstride;
+  g.Y = panel - r0 * 64; g.y_kstride = pstride;
+  g.C = A; g.c_cstride = cstride;
+  g.mode = 1; g.rb0 = rb0; g.world = p->world; g.rank = p->rank;
+  LCU(ctx, cudaFuncSetAttribute(large_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_SMEM));
+  const long long ncb = (l_hi - l_lo) * (LG_BT / LG_BLK);
+  for (long long y0 = 0; y0 < ncb; y0 += 65535) {
+    g.lcb0 = (int)(l_lo * (LG_BT / LG_BLK) + y0);
+    const unsigned ny = (unsigned)std::min<long long>(65535, ncb - y0);
+    cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+    large_gemm_kernel<<<dim3((unsigned)(RB - rb0), ny), LG_THREADS, LG_SMEM, s>>>(g);
+    cngp_ctx_end(ctx);
+  }
+  LCU(ctx, cudaGetLastError());
+  return CNGP_OK;
+}
+
+extern "C" int cngp_large_reduce(cngp_ctx* ctx, const cngp_large_plan* p, const double* A, const double* logdet,
+                                 const int32_t* status, double* z, double* sums) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!p || !A || !logdet || !status || !z || !sums) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_reduce: bad argument");
+  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
+  cudaStream_t s = cngp_ctx_stream(ctx);
+  LCU(ctx, cudaMemsetAsync(z, 0, sizeof(double) * (size_t)p->n_pad, s));
+  cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+  large_reduce_kernel<<<1, 1024, 0, s>>>(A, p->row_tiles, p->n_pad / 8, p->n_local_blockcols * LG_BT, p->world, p->rank,
+                                         logdet, status, p->n_blockcols, z, sums);
+  cngp_ctx_end(ctx);
+  LCU(ctx, cudaGetLastError());
+  return CNGP_OK;
+}
+
+extern "C" int cngp_large_backsolve_step(cngp_ctx* ctx, const cngp_large_plan* p, const double* A, const double* winv,
+                                         int64_t j, const double* z, double* alpha) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!p || !A || !winv || !z || !alpha || j < 0 || j >= p->n_blockcols)
+    return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_backsolve_step: bad argument");
+  if (j % p->world != p->rank) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_backsolve_step: not the owner");
+  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
+  cudaStream_t s = cngp_ctx_stream(ctx);
+  double* partial = (double*)cngp_ctx_buf(ctx, SLOT_PARTIAL, sizeof(double) * BACK_CHUNKS * LG_NB);
+  if (!partial) return cngp_set_error(ctx, CNGP_ERR_NOMEM, "large_backsolve_step: scratch");
+  const long long l = j / p->world;
+  const long long cstride = p->row_tiles * 64;
+  const double* Acol = A + l * LG_BT * cstride;
+  const long long NT = p->n_pad / 8;
+  cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+  large_back_partial_kernel<<<dim3(LG_BT, BACK_CHUNKS), 256, 0, s>>>(Acol, p->row_tiles, (j + 1) * LG_BT, NT, alpha, partial);
+  cngp_ctx_end(ctx);
+  cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+  large_back_finish_kernel<<<1, LG_NB, 0, s>>>(winv + l * LG_BT * LG_BT * 64, z + j * LG_NB, partial, alpha + j * LG_NB);
+  cngp_ctx_end(ctx);
+  LCU(ctx, cudaGetLastError());
+  return CNGP_OK;
+}
+
+extern "C" int cngp_large_matvec(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, const double* x,
+                                 const double* v, int64_t N, double* r) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!kernel || !theta || !x || !v || !r || N <= 0) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_matvec: bad argument");
+  KProg kp;
+  int rc = cngp_build_kprog(kernel, &kp);
+  if (rc) return cngp_set_error(ctx, rc, "large_matvec: invalid kernel expression");
+  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
+  cudaStream_t s = cngp_ctx_stream(ctx);
+  double* d_theta = (double*)cngp_ctx_buf(ctx, SLOT_THETA, sizeof(double) * (CNGP_MAX_PARAMS + 1));
+  if (!d_theta) return cngp_set_error(ctx, CNGP_ERR_NOMEM, "large_matvec: theta buffer");
+  LCU(ctx, cudaMemcpyAsync(d_theta, theta, sizeof(double) * (kp.n_params + 1), cudaMemcpyHostToDevice, s));
+  LCU(ctx, cudaStreamSynchronize(s));
+  cngp_ctx_begin(ctx, CNGP_PROF_MISC);
+  dispatch_kid(match_fast_kernel(kp), [&](auto kid) {
+    large_matvec_kernel<decltype(kid)::value><<<(unsigned)((N + 7) / 8), 256, 0, s>>>(kp, d_theta, x, v, N, r);
+  });
+  cngp_ctx_end(ctx);
+  LCU(ctx, cudaGetLastError());
+  return CNGP_OK;
+}
+
+namespace {
+struct DevMem {
+  void* p = nullptr;
+  ~DevMem() { if (p) cudaFree(p); }
+  bool alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)) == cudaSuccess; }
+};
+}  // namespace
+
+extern "C" int cngp_chol_large(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, const double* x,
+                               const double* y, int64_t N, double* logdet, double* quad, double* lml, double* alpha,
+                               int32_t mem) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!kernel || !theta || !x || !y || N <= 0) return cngp_set_error(ctx, CNGP_ERR_INVALID, "chol_large: bad argument");
+  cngp_large_plan p;
+  cngp_large_make_plan(N, 1, 0, &p);
+  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
+  cudaStream_t s = cngp_ctx_stream(ctx);
+  DevMem dA, dP, dW, dld, dst, dz, dal, dsum, dx, dy;
+  if (!dA.alloc(sizeof(double) * p.local_doubles) || !dP.alloc(sizeof(double) * p.panel_doubles) ||
+      !dW.alloc(sizeof(double) * p.winv_doubles) || !dld.alloc(sizeof(double) * p.n_blockcols) ||
+      !dst.alloc(sizeof(int) * p.n_blockcols) || !dz.alloc(sizeof(double) * p.n_pad) ||
+      !dal.alloc(sizeof(double) * p.n_pad) || !dsum.alloc(sizeof(double) * 4))
+    return cngp_set_error(ctx, CNGP_ERR_NOMEM, "chol_large: device allocation failed");
+  const double *d_x = x, *d_y = y;
+  if (mem == CNGP_MEM_HOST) {
+    if (!dx.alloc(sizeof(double) * N) || !dy.alloc(sizeof(double) * N))
+      return cngp_set_error(ctx, CNGP_ERR_NOMEM, "chol_large: device allocation failed");
+    LCU(ctx, cudaMemcpyAsync(dx.p, x, sizeof(double) * N, cudaMemcpyHostToDevice, s));
+    LCU(ctx, cudaMemcpyAsync(dy.p, y, sizeof(double) * N, cudaMemcpyHostToDevice, s));
+    d_x = (const double*)dx.p; d_y = (const double*)dy.p;
+  }
+  int rc = cngp_large_assemble(ctx, &p, kernel, theta, d_x, d_y, (double*)dA.p);
+  if (rc) return rc;
+  LCU(ctx, cudaMemsetAsync(dP.p, 0, sizeof(double) * p.panel_doubles, s));
+  for (int64_t k = 0; k < p.n_blockcols; ++k) {
+    if ((rc = cngp_large_factor_panel(ctx, &p, (double*)dA.p, k, (double*)dP.p, (double*)dW.p, (double*)dld.p, (int*)dst.p))) return rc;
+    if ((rc = cngp_large_update(ctx, &p, (double*)dA.p, k, (const double*)dP.p, k + 1, p.n_blockcols))) return rc;
+  }
+  if ((rc = cngp_large_reduce(ctx, &p, (const double*)dA.p, (const double*)dld.p, (const int*)dst.p, (double*)dz.p, (double*)dsum.p))) return rc;
+  if (alpha) {
+    LCU(ctx, cudaMemsetAsync(dal.p, 0, sizeof(double) * p.n_pad, s));
+    for (int64_t j = p.n_blockcols - 1; j >= 0; --j)
+      if ((rc = cngp_large_backsolve_step(ctx, &p, (const double*)dA.p, (const double*)dW.p, j, (const double*)dz.p, (double*)dal.p))) return rc;
+    LCU(ctx, cudaMemcpyAsync(alpha, dal.p, sizeof(double) * N, mem == CNGP_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
+  }
+  double sums[3];
+  LCU(ctx, cudaMemcpyAsync(sums, dsum.p, sizeof sums, cudaMemcpyDeviceToHost, s));
+  LCU(ctx, cudaStreamSynchronize(s));
+  const bool bad = sums[2] != 0.0;
+  const double nanv = std::nan("");
+  if (logdet) *logdet = bad ? nanv : sums[0];
+  if (quad) *quad = bad ? nanv : sums[1];
+  if (lml) *lml = bad ? nanv : 0.5 * (-(double)N * CNGP_LOG_2PI - sums[0] - sums[1]);
+  return bad ? (int)sums[2] : CNGP_OK;
+}

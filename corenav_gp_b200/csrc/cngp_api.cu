@@ -103,6 +103,12 @@ static int fail(cngp_ctx* c, int code, const char* fmt, ...) {
 }
 
 int cngp_set_error(cngp_ctx* ctx, int code, const char* text) { return fail(ctx, code, "%s", text); }
+cudaStream_t cngp_ctx_stream(cngp_ctx* ctx) { return ctx->stream; }
+int cngp_ctx_device(cngp_ctx* ctx) { return ctx->cfg.device; }
+void cngp_ctx_begin(cngp_ctx* ctx, int prof_id) { ctx->begin(prof_id); }
+void cngp_ctx_end(cngp_ctx* ctx) { ctx->end(); }
+void* cngp_ctx_buf(cngp_ctx* ctx, size_t slot, size_t bytes) { return ctx->buf(slot, bytes); }
+int cngp_sm_count(void) { return g_sm_count; }
 
 #define CU(c, call)                                                                                  \
   do {                                                                                               \
@@ -245,6 +251,7 @@ static int build_kprog(const cngp_kernel* k, KProg* kp) {
   kp->fast_id = 0;
   return CNGP_OK;
 }
+int cngp_build_kprog(const cngp_kernel* k, cngp::KProg* kp) { return build_kprog(k, kp); }
 
 // ------------------------------------------------------------------------------------------------------------
 // context
@@ -470,6 +477,7 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
     fa.L = Lbuf; fa.z = zbuf; fa.feat = fbuf; fa.lml = d_lml; fa.logdet = nullptr; fa.quad = nullptr;
     fa.status = d_status;
     fa.jitter_retry = ctx->cfg.jitter_retry;
+    fa.Asrc = nullptr; fa.a_col_stride = 0;
     ctx->begin(CNGP_PROF_FIT);
     launch_fit(kid, fa, nw, ctx->stream);
     ctx->end();
@@ -553,6 +561,7 @@ int cngp_lml_grad_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* t
     fa.L = Lbuf; fa.z = zbuf; fa.feat = nullptr; fa.lml = d_lml; fa.logdet = nullptr; fa.quad = nullptr;
     fa.status = d_status;
     fa.jitter_retry = ctx->cfg.jitter_retry;
+    fa.Asrc = nullptr; fa.a_col_stride = 0;
     ctx->begin(CNGP_PROF_FIT);
     launch_fit(match_fast_kernel(kp), fa, np, ctx->stream);
     ctx->end();

@@ -14,3 +14,16 @@ int cngp_lml_grad_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* t
 
 // error text of a context (cngp_api.cu)
 int cngp_set_error(cngp_ctx* ctx, int code, const char* text);
+
+// ---- context internals for the other translation units (chol_large.cu) ----
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+namespace cngp { struct KProg; }
+cudaStream_t cngp_ctx_stream(cngp_ctx* ctx);
+int cngp_ctx_device(cngp_ctx* ctx);
+void cngp_ctx_begin(cngp_ctx* ctx, int prof_id);   // counts one kernel launch (+ opens a timing span when profiling)
+void cngp_ctx_end(cngp_ctx* ctx);
+void* cngp_ctx_buf(cngp_ctx* ctx, size_t slot, size_t bytes);   // grow-only device buffer `slot`
+int cngp_build_kprog(const cngp_kernel* k, cngp::KProg* kp);
+int cngp_sm_count(void);
+#endif

@@ -48,6 +48,10 @@ struct FitArgs {
   double* quad;          // [n_problems] or null   y' Ky^-1 y
   int* status;           // [n_problems] or null
   int jitter_retry;
+  // KID_TILES only (large-N blocked Cholesky, chol_large.cu): the SPD block is read from tile storage instead of being
+  // evaluated - tile (i, j) of the block at Asrc + j * a_col_stride + i * 64 (lower tiles only are read).
+  const double* Asrc;
+  long long a_col_stride;
 };
 
 // In-warp Cholesky of an 8x8 SPD tile held in the lane layout, followed by the inverse of the factor.  This sits on
@@ -127,15 +131,15 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) gp_fit_kernel(const FitArgs a)
   const double* th = a.theta + ti * a.theta_stride;
   const int N = a.N, nt = a.nt;
   const int h = (nt + 1) / 2, nb = nt - h;          // tile rows of the top block / bottom block
-  const double noise = th[a.kp.n_params];
+  const double noise = (KID == KID_TILES) ? 0.0 : th[a.kp.n_params];
   FastK<KID> fk;
-  if (KID != KID_GENERIC) fk.init(th);
+  if (KID != KID_GENERIC && KID != KID_TILES) fk.init(th);
 
   for (int i = tid; i < nt * 8; i += FIT_THREADS) {
-    const double xv = i < N ? a.x[(long long)win * N + i] : 0.0;
-    ys[i] = i < N ? a.y[(long long)win * N + i] : 0.0;
+    const double xv = (KID != KID_TILES && i < N) ? a.x[(long long)win * N + i] : 0.0;
+    ys[i] = (KID != KID_TILES && i < N) ? a.y[(long long)win * N + i] : 0.0;
     PointFeat f{xv, __dmul_rn(xv, xv), 0.0, 0.0};
-    if (KID != KID_GENERIC) f = fk.point(xv);
+    if (KID != KID_GENERIC && KID != KID_TILES) f = fk.point(xv);
     fx[i] = f.x; fxx[i] = f.xx; fc[i] = f.c; fs[i] = f.s;
     if (a.feat) {
       double* fp = a.feat + lp * (long long)(4 * nt * 8);
@@ -150,6 +154,7 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) gp_fit_kernel(const FitArgs a)
 
   // Ky(row, col) from the staged features; identity padding beyond N
   auto ky_entry = [&](int row, int col, const PointFeat& fa, const PointFeat& fb) -> double {
+    if (KID == KID_TILES) return 0.0;   // never used: the tiles are loaded below
     if (row < N && col < N) {
       if (KID == KID_GENERIC) return keval_generic_sym(&kps, hc, fa.x, fb.x, row == col);
       return fk.eval(fa, fb, row == col);
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) gp_fit_kernel(const FitArgs a)
   double* Lp = a.L + lp * (long long)tiles_in_lower(nt) * 64;
   double* poolA = pool + 2 * lane;                       // lane-offset views of the two pool regions
   double* poolB = pool + (h * (h + 1) / 2) * 64 + 2 * lane;
-  const int max_attempts = a.jitter_retry ? 6 : 1;
+  const int max_attempts = (a.jitter_retry && KID != KID_TILES) ? 6 : 1;
   double extra = 0.0;
   int fail_pivot = 0, attempts_used = 0;
 
@@ -264,10 +269,17 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) gp_fit_kernel(const FitArgs a)
         for (int t = 0; t < FIT_MAXT; ++t) {
           if (t < nvalid) {
             const int row = 8 * (j + w + FIT_WARPS * t) + r;
-            const PointFeat fr = feat_at(row);
-            double v0 = ky_entry(row, c0, fr, fc0), v1 = ky_entry(row, c1, fr, fc1);
-            if (row == c0 && row < N) v0 += dadd;
-            if (row == c1 && row < N) v1 += dadd;
+            double v0, v1;
+            if (KID == KID_TILES) {
+              const double2 av = *reinterpret_cast<const double2*>(
+                  a.Asrc + j * a.a_col_stride + (long long)(j + w + FIT_WARPS * t) * 64 + 2 * lane);
+              v0 = av.x; v1 = av.y;
+            } else {
+              const PointFeat fr = feat_at(row);
+              v0 = ky_entry(row, c0, fr, fc0); v1 = ky_entry(row, c1, fr, fc1);
+              if (row == c0 && row < N) v0 += dadd;
+              if (row == c1 && row < N) v1 += dadd;
+            }
             S[t].a = v0 - S[t].a;
             S[t].b = v1 - S[t].b;
           }

@@ -61,7 +61,7 @@ struct VarShared {
 
 // Load the chunk under the producer cursor into `slot` and advance the cursor.  Called by one lane at a time (the
 // prologue, then whichever lane performed the last release of a slot); kept out of line: it is the rare path.
-__device__ __noinline__ void var_issue_next(VarShared* sh, int slot) {
+static __device__ __noinline__ void var_issue_next(VarShared* sh, int slot) {
   const int it = sh->cur_it;
   if (it >= sh->nwin_cta) return;
   const int ce = sh->cur_ce;

@@ -180,6 +180,7 @@ __host__ __device__ __forceinline__ int leaf_nparams(int type) {
 //   KID 3  rbf * brownian            (the deployed kernel, gp_slip_node.py:31)
 // ------------------------------------------------------------------------------------------------------------
 constexpr int KID_GENERIC = 0, KID_RBF = 1, KID_RBF_PER = 2, KID_RBF_BROWN = 3;
+constexpr int KID_TILES = 4;   // gp_fit_kernel only: factor a block held as tiles in global memory (chol_large.cu)
 
 // exp(x) for x <= ~1 (kernel exponents are never positive); flushes to 0 below -708.
 __device__ __forceinline__ double fast_exp(double x) {
@@ -259,10 +260,10 @@ struct FastK {
 
 // Uniform front end used by the kernels: KID 0 forwards to the interpreter (kept out of line so the unrolled
 // callers stay small), KID > 0 to FastK.
-__device__ __noinline__ double keval_generic_sym(const KProg* kp, const LeafConst* hc, double xa, double xb, bool same) {
+static __device__ __noinline__ double keval_generic_sym(const KProg* kp, const LeafConst* hc, double xa, double xb, bool same) {
   return keval<true>(*kp, hc, xa, xb, same);
 }
-__device__ __noinline__ double keval_generic_cross(const KProg* kp, const LeafConst* hc, double xa, double xb) {
+static __device__ __noinline__ double keval_generic_cross(const KProg* kp, const LeafConst* hc, double xa, double xb) {
   return keval<false>(*kp, hc, xa, xb, false);
 }
 

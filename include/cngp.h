@@ -192,10 +192,55 @@ int cngp_zupt_lookahead_batch(cngp_ctx* ctx, const double* mean, const double* s
 /* GpPredictor::llh_to_enu for n points on the device (lat, lon, h -> E, N, U); llh, enu [n][3]. */
 int cngp_llh_to_enu(cngp_ctx* ctx, const double* llh, int64_t n, const cngp_stop_config* cfg, double* enu, int32_t mem);
 
-/* ---- large single window (BASELINE.json configs[4]) ----
- * Blocked right-looking FP64 Cholesky of Ky = K(x,x) + (noise + 1e-8) I assembled on the device; returns
- * logdet, y' Ky^-1 y and lml; alpha [N] (may be NULL).  Single GPU; the multi-GPU block-cyclic driver lives in
- * corenav_gp_b200/large.py on top of cngp_chol_large_* panel primitives. */
+/* ---- large single window (BASELINE.json configs[4]: N = 32768) ----
+ * Blocked right-looking FP64 Cholesky of Ky = K(x,x) + (noise + 1e-8) I - the same inference as cngp_predict_batch
+ * (row a3: GPy ExactGaussianInference as reached from gp_slip_node.py:35) for a window too large for shared memory.
+ * The matrix lives in HBM as 8x8 tiles, column-tile-major, in block columns of CNGP_LARGE_NB columns dealt
+ * cyclically to `world` GPUs (block column c belongs to rank c % world).  Per block column k: the owner factors the
+ * diagonal block, inverts it and forms the panel (rows below) - cngp_large_factor_panel; the panel buffer is then
+ * broadcast (NCCL, by the caller: corenav_gp_b200/large.py) and every rank subtracts panel x panel^T from its own
+ * block columns - cngp_large_update, the only dense contraction (FP64 tensor cores fed by bulk-TMA copies).  y rides
+ * along as one extra matrix row, so z = L^-1 y, y' Ky^-1 y and the LML come out of the factorisation itself.
+ * All pointers of the cngp_large_* primitives are DEVICE pointers except `theta` and the plan. */
+#define CNGP_LARGE_NB 256
+typedef struct cngp_large_plan {
+  int64_t N;                 /* training points */
+  int64_t n_pad;             /* N rounded up to a multiple of CNGP_LARGE_NB (identity padding) */
+  int32_t world, rank;
+  int64_t row_tiles;         /* allocated 8-row tiles per column tile: n_pad/8 + 16; tile n_pad/8 carries y / z */
+  int64_t n_blockcols;       /* n_pad / CNGP_LARGE_NB */
+  int64_t n_local_blockcols; /* block columns of this rank */
+  int64_t local_doubles;     /* size of this rank's matrix storage A */
+  int64_t panel_doubles;     /* size of one panel buffer */
+  int64_t winv_doubles;      /* inverted diagonal blocks of the local block columns (kept for the back substitution) */
+} cngp_large_plan;
+int cngp_large_make_plan(int64_t N, int32_t world, int32_t rank, cngp_large_plan* plan);
+/* Fill this rank's block columns: Ky tiles on and below the diagonal blocks, the y row, identity padding. */
+int cngp_large_assemble(cngp_ctx* ctx, const cngp_large_plan* plan, const cngp_kernel* kernel, const double* theta,
+                        const double* x, const double* y, double* A);
+/* Owner of block column k: factor + invert the diagonal block, panel = rows below x inv(L_kk)^T, written to `panel`
+ * and back into A.  The panel buffer is compact: with r0 = (k+1) NB/8 and R = row_tiles - r0, tile (k-tile kt, row tile
+ * rt >= r0) is at panel[(kt R + rt - r0) 64], so the first (NB/8) R 64 doubles are what the other ranks need.  logdet[k] = log det of the diagonal block; status[k] = 0 or -(failing pivot, 1-based in block). */
+int cngp_large_factor_panel(cngp_ctx* ctx, const cngp_large_plan* plan, double* A, int64_t k, double* panel,
+                            double* winv, double* logdet, int32_t* status);
+/* Every rank: A(:, c) -= panel panel(c)^T for its block columns c in [max(c_lo, k+1), c_hi). */
+int cngp_large_update(cngp_ctx* ctx, const cngp_large_plan* plan, double* A, int64_t k, const double* panel,
+                      int64_t c_lo, int64_t c_hi);
+/* After the last panel: z [n_pad] (this rank's columns, 0 elsewhere), sums[0] = sum of this rank's logdet[k],
+ * sums[1] = sum of this rank's z^2, sums[2] = first failing pivot (1-based, global) of this rank's blocks or 0. */
+int cngp_large_reduce(cngp_ctx* ctx, const cngp_large_plan* plan, const double* A, const double* logdet,
+                      const int32_t* status, double* z, double* sums);
+/* One step of alpha = L^-T z, last block column first: the owner of block column j computes alpha[j NB .. (j+1) NB)
+ * from z and alpha of the later blocks (which must already be in `alpha` on this rank). */
+int cngp_large_backsolve_step(cngp_ctx* ctx, const cngp_large_plan* plan, const double* A, const double* winv,
+                              int64_t j, const double* z, double* alpha);
+/* r = Ky v for the same covariance, evaluated on the fly (no matrix stored): the residual check of the solve. */
+int cngp_large_matvec(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, const double* x, const double* v,
+                      int64_t N, double* r);
+
+/* The whole single-GPU sequence: assemble, factor, logdet, quad = y' Ky^-1 y, lml, alpha = Ky^-1 y [N] (may be NULL).
+ * x, y, alpha follow `mem`; logdet/quad/lml are HOST scalars (may be NULL).  Returns CNGP_OK, or a positive value
+ * = the (1-based) pivot at which the factorisation broke down. */
 int cngp_chol_large(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, const double* x, const double* y,
                     int64_t N, double* logdet, double* quad, double* lml, double* alpha, int32_t mem);
 
