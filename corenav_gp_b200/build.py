@@ -17,6 +17,8 @@ LIB = os.path.join(HERE, "libcngp.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+if os.environ.get("CNGP_VAR_TUNE"):   # tuning builds: extra gp_var_kernel group shapes (CNGP_VAR_VARIANT at run time)
+    COMMON.append("-DCNGP_VAR_TUNE")
 
 # translation unit -> extra flags
 UNITS = {

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -389,22 +390,29 @@ struct Stage {
 // ------------------------------------------------------------------------------------------------------------
 // batched predict
 // ------------------------------------------------------------------------------------------------------------
-template <int NT_MAX, int WARPS, int KID>
-static void launch_var_k(const VarArgs& va, long long nwin, cudaStream_t s) {
-  const long long grid = std::min<long long>(nwin, g_sm_count);   // persistent: one CTA per SM
-  const size_t smem = var_smem_bytes(WARPS);
+template <int NT_MAX, int G, int WG, int NSLOT, int CT, int KID>
+static int launch_var_k(cngp_ctx* ctx, VarArgs& va, long long nwin, cudaStream_t s) {
+  const long long nrounds = (va.mt + WG - 1) / WG;
+  const long long units = nwin * nrounds;
+  const long long grid = std::min<long long>((units + G - 1) / G, g_sm_count);   // persistent: one CTA per SM
+  const size_t smem = var_smem_bytes(G, WG, NSLOT, CT);
+  if (KID == KID_GENERIC) {
+    va.kstage = (double*)ctx->buf(12, (size_t)grid * G * WG * NT_MAX * 64 * sizeof(double));
+    if (!va.kstage) return CNGP_ERR_NOMEM;
+  }
   const bool full = va.nt == NT_MAX && va.N == NT_MAX * 8;
-  auto kfn = full ? gp_var_kernel<NT_MAX, WARPS, KID, true> : gp_var_kernel<NT_MAX, WARPS, KID, false>;
+  auto kfn = full ? gp_var_kernel<NT_MAX, G, WG, NSLOT, CT, KID, true> : gp_var_kernel<NT_MAX, G, WG, NSLOT, CT, KID, false>;
   cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kfn<<<(unsigned)grid, WARPS * 32, smem, s>>>(va);
+  kfn<<<(unsigned)grid, G * WG * 32, smem, s>>>(va);
+  return CNGP_OK;
 }
-template <int NT_MAX, int WARPS>
-static void launch_var(int kid, const VarArgs& va, long long nwin, cudaStream_t s) {
+template <int NT_MAX, int G, int WG, int NSLOT, int CT>
+static int launch_var(cngp_ctx* ctx, int kid, VarArgs& va, long long nwin, cudaStream_t s) {
   switch (kid) {
-    case KID_RBF: launch_var_k<NT_MAX, WARPS, KID_RBF>(va, nwin, s); break;
-    case KID_RBF_PER: launch_var_k<NT_MAX, WARPS, KID_RBF_PER>(va, nwin, s); break;
-    case KID_RBF_BROWN: launch_var_k<NT_MAX, WARPS, KID_RBF_BROWN>(va, nwin, s); break;
-    default: launch_var_k<NT_MAX, WARPS, KID_GENERIC>(va, nwin, s); break;
+    case KID_RBF: return launch_var_k<NT_MAX, G, WG, NSLOT, CT, KID_RBF>(ctx, va, nwin, s);
+    case KID_RBF_PER: return launch_var_k<NT_MAX, G, WG, NSLOT, CT, KID_RBF_PER>(ctx, va, nwin, s);
+    case KID_RBF_BROWN: return launch_var_k<NT_MAX, G, WG, NSLOT, CT, KID_RBF_BROWN>(ctx, va, nwin, s);
+    default: return launch_var_k<NT_MAX, G, WG, NSLOT, CT, KID_GENERIC>(ctx, va, nwin, s);
   }
 }
 template <int KID, int WARPS>
@@ -462,7 +470,7 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
   const int nt = (N + 7) / 8, mt = (M + 7) / 8;
   const int kid = match_fast_kernel(kp);
   const size_t per_problem = ((size_t)tiles_in_lower(nt) * 64 + (size_t)nt * 8 * 5) * sizeof(double);
-  const size_t slack = VAR_CHUNK_DOUBLES;   // gp_var_kernel's first (partial) chunk may start before the first tile
+  const size_t slack = 64 * 64;   // >= the largest chunk (tiles x 64 doubles)   // gp_var_kernel's first (partial) chunk may start before the first tile
   const long long chunk = std::max<long long>(1, (long long)((ctx->scratch_bytes - slack * 8) / per_problem));
   for (long long w0 = 0; w0 < B; w0 += chunk) {
     const long long nw = std::min<long long>(chunk, B - w0);
@@ -489,11 +497,19 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
       va.N = N; va.nt = nt; va.M = M; va.mt = mt; va.window0 = w0; va.n_windows_launch = nw;
       va.L = Lbuf; va.z = zbuf; va.feat = fbuf; va.status = d_status; va.mean = d_mean; va.var = d_var;
       va.sigma_mode = sigma_mode;
+      va.kstage = nullptr;
       ctx->begin(CNGP_PROF_VAR);
-      if (nt <= 8) launch_var<8, 16>(kid, va, nw, ctx->stream);
-      else if (nt <= 16) launch_var<16, 16>(kid, va, nw, ctx->stream);
-      else launch_var<32, 12>(kid, va, nw, ctx->stream);
+      int vrc;
+      if (nt <= 8) vrc = launch_var<8, 1, 16, 6, 16>(ctx, kid, va, nw, ctx->stream);
+      else if (nt <= 16) vrc = launch_var<16, 1, 16, 6, 16>(ctx, kid, va, nw, ctx->stream);
+#ifdef CNGP_VAR_TUNE   // tuning builds only: alternative shapes selected by the environment
+      else if (getenv("CNGP_VAR_VARIANT") && atoi(getenv("CNGP_VAR_VARIANT")) == 1) vrc = launch_var<32, 1, 12, 4, 32>(ctx, kid, va, nw, ctx->stream);
+      else if (getenv("CNGP_VAR_VARIANT") && atoi(getenv("CNGP_VAR_VARIANT")) == 2) vrc = launch_var<32, 1, 12, 6, 32>(ctx, kid, va, nw, ctx->stream);
+      else if (getenv("CNGP_VAR_VARIANT") && atoi(getenv("CNGP_VAR_VARIANT")) == 3) vrc = launch_var<32, 1, 12, 8, 16>(ctx, kid, va, nw, ctx->stream);
+#endif
+      else vrc = launch_var<32, 1, 12, 3, 64>(ctx, kid, va, nw, ctx->stream);
       ctx->end();
+      if (vrc) return fail(ctx, vrc, "predict: staging buffer for the generic kernel path");
     }
     CU(ctx, cudaGetLastError());
   }

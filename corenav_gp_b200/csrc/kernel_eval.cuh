@@ -209,6 +209,51 @@ __device__ __forceinline__ double fast_exp(double x) {
   return __hiloint2double(hi, lo);
 }
 
+// Table-driven exp for the assembly hot loops: exp(x) = 2^e * T[j] * (1 + r h(r)),  64 e + j = round(64 x / ln 2),
+// |r| <= ln2/128, h = degree-4 Taylor of (e^r - 1)/r (truncation 3.5e-17).  Nine FP64 operations instead of sixteen;
+// the table (2^(j/64), correctly rounded) is read from shared memory where the caller has pre-multiplied it by the
+// leaf variance, which also removes the final multiply.  The reduction uses a single constant: its absolute error is
+// <= 1.1e-16 |x| e^x <= 4e-17, below the rounding of the near-diagonal entries.  Valid for x <= ~1; x < -600 -> 0.
+__device__ const double EXP2_TAB64[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+
+__device__ __forceinline__ double exp_tab(double x, const double* tab) {
+  const double magic = 6755399441055744.0;                     // 1.5 * 2^52
+  const double t = fma(x, 92.33248261689366, magic);           // 64 / ln 2
+  const int n = __double2loint(t);
+  const double nd = t - magic;
+  const double r = fma(nd, -0.010830424696249145, x);          // ln 2 / 64
+  double h = fma(r, 8.33333333333333333e-03, 4.16666666666666667e-02);
+  h = fma(h, r, 1.66666666666666667e-01);
+  h = fma(h, r, 0.5);
+  h = fma(h, r, 1.0);
+  const double T = tab[n & 63];
+  const double res = fma(T * r, h, T);
+  // scale by 2^(n >> 6) through the exponent field, flush to zero for x < -600.  The selects are opaque inline asm
+  // on purpose: written as C++ conditionals the compiler turns them into a BRANCH around the polynomial, which makes
+  // every exp its own basic block and stops the scheduler from interleaving the evaluations with the DMMA stream.
+  int hi = __double2hiint(res) + ((n >> 6) << 20), lo = __double2loint(res);
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %2, 0xC082C000;\n\tselp.b32 %0, 0, %0, p;\n\tselp.b32 %1, 0, %1, p;\n\t}"
+      : "+r"(hi), "+r"(lo)
+      : "r"(__double2hiint(x)));
+  return __hiloint2double(hi, lo);
+}
+
 struct PointFeat {
   double x, xx, c, s;  // x, x*x, cos(2 pi x / p), sin(2 pi x / p)
 };
@@ -250,6 +295,21 @@ struct FastK {
     // rbf * brownian
     const bool agree = (a.x > 0.0 && b.x > 0.0) || (a.x < 0.0 && b.x < 0.0) || (a.x == 0.0 && b.x == 0.0);
     return agree ? e1 * (c4 * fmin(fabs(a.x), fabs(b.x))) : 0.0;
+  }
+  // Table variant (exp_tab): tab[0..63] = scale1() 2^(j/64), tab[64..127] = scale2() 2^(j/64), built by the caller.
+  __device__ __forceinline__ double scale1() const { return KID == KID_RBF_BROWN ? c0 * c4 : c0; }
+  __device__ __forceinline__ double scale2() const { return KID == KID_RBF_PER ? c4 : 0.0; }
+  __device__ __forceinline__ double eval_tab(const PointFeat& a, const PointFeat& b, bool same_sym, const double* tab) const {
+    double rr = r2(a, b);
+    if (same_sym) rr = 0.0;
+    const double e1 = exp_tab(rr * c1, tab);
+    if (KID == KID_RBF) return e1;
+    if (KID == KID_RBF_PER) {
+      const double cd = fma(a.c, b.c, a.s * b.s);          // cos(phi_a - phi_b)
+      return e1 + exp_tab(fma(c3, cd, -c3), tab + 64);
+    }
+    const bool agree = (a.x > 0.0 && b.x > 0.0) || (a.x < 0.0 && b.x < 0.0) || (a.x == 0.0 && b.x == 0.0);
+    return agree ? e1 * fmin(fabs(a.x), fabs(b.x)) : 0.0;
   }
   __device__ __forceinline__ double kdiag(double x) const {
     if (KID == KID_RBF) return c0;
