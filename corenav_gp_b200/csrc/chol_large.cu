@@ -508,7 +508,7 @@ extern "C" int cngp_large_factor_panel(cngp_ctx* ctx, const cngp_large_plan* p, 
   const size_t smem = fit_smem_bytes(LG_BT);
   LCU(ctx, cudaFuncSetAttribute(gp_fit_kernel<KID_TILES, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
-  gp_fit_kernel<KID_TILES, 16><<<1, 16 * 32, smem, s>>>(fa);
+  gp_fit_kernel<KID_TILES, 16><<<1, 17 * 32, smem, s>>>(fa);   // 16 workers + the diagonal warp
   cngp_ctx_end(ctx);
   // 2. inverse of the block factor
   cngp_ctx_begin(ctx, CNGP_PROF_LARGE);

@@ -419,12 +419,13 @@ template <int KID, int WARPS>
 static void launch_fit_k(const FitArgs& fa, long long nprob, cudaStream_t s) {
   const size_t smem = fit_smem_bytes(fa.nt);
   cudaFuncSetAttribute(gp_fit_kernel<KID, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  gp_fit_kernel<KID, WARPS><<<(unsigned)nprob, WARPS * 32, smem, s>>>(fa);
+  gp_fit_kernel<KID, WARPS><<<(unsigned)nprob, (WARPS + 1) * 32, smem, s>>>(fa);   // WARPS workers + the diagonal warp
 }
 template <int KID>
 static void launch_fit_w(const FitArgs& fa, long long nprob, cudaStream_t s) {
-  // row tiles per column <= nt + 1 must fit WARPS * FIT_MAXT
-  if (fa.nt + 1 <= 8 * FIT_MAXT) launch_fit_k<KID, 8>(fa, nprob, s);
+  // row tiles per column (nt) must fit WARPS * FIT_MAXT
+  if (fa.nt <= 4 * FIT_MAXT) launch_fit_k<KID, 4>(fa, nprob, s);
+  else if (fa.nt <= 8 * FIT_MAXT) launch_fit_k<KID, 8>(fa, nprob, s);
   else launch_fit_k<KID, 16>(fa, nprob, s);
 }
 static void launch_fit(int kid, const FitArgs& fa, long long nprob, cudaStream_t s) {

@@ -3,10 +3,22 @@
 // Replaces GPy ExactGaussianInference.inference as reached from GPRegression(...) at
 // core_navigation/script/gp_slip_node.py:35 (row a3): kern.K, pdinv -> jitchol -> dpotrf, dpotrs, logdet.
 //
-// One CTA per (candidate, window) problem.  Left-looking tile Cholesky over 8-wide tile columns; every update,
-// the triangular solve below the diagonal (through the explicitly inverted 8x8 diagonal tile) and the forward solve
-// for z (carried as an extra 1-row "tile row" under the matrix) are tile_mma = FP64 DMMA.  The kernel matrix is
-// never materialised: each 8x8 tile of Ky is evaluated in registers at the moment its column becomes current.
+// One CTA per (candidate, window) problem: NW worker warps + one DIAGONAL warp.  Left-looking tile Cholesky over
+// 8-wide tile columns with a one-column look-ahead, so that the only serial chain of the algorithm - the in-warp
+// factorisation + inversion of the 8x8 diagonal tile (chol8_inv8, ~1.3k cycles of dependent shuffles / rsqrt / fma
+// per column) - runs on the diagonal warp WHILE the workers accumulate the bulk of the next column:
+//
+//   workers, column j:  (b) S(i, j+1) = sum_{k<j} L(i,k) L(j+1,k)^T  for their rows of column j+1, evaluate Ky(i, j+1)
+//                           (the kernel matrix is never materialised), park the diagonal row's partial sum in smem
+//                       --- barrier 1: inv(L_jj) published by the diagonal warp ---
+//                       (d) L(i,j) = C(i,j) inv(L_jj)^T  -> tile pool (for later columns) and global (for phase B)
+//                       --- barrier 2 ---
+//                       (a) C(i, j+1) = Ky(i, j+1) - S(i, j+1) - L(i,j) L(j+1,j)^T
+//   diagonal warp:      chol8_inv8(C(j,j)) -> inv(L_jj); arrive on barrier 1; wait on barrier 2;
+//                       C(j+1,j+1) = parked partial - L(j+1,j) L(j+1,j)^T.
+//
+// Every update, the triangular solve below the diagonal (through the explicitly inverted 8x8 diagonal tile) and the
+// forward solve for z (carried as an extra 1-row "tile row" under the matrix) are tile_mma = FP64 DMMA.
 // Output factor layout (consumed by gp_var.cuh / gp_grad.cuh): column-block-major tiles, tile (j,j) holds
 // inv(L_jj) (lower triangular), tiles (i>j, j) hold L_ij.
 #pragma once
@@ -14,7 +26,7 @@
 
 namespace cngp {
 
-constexpr int FIT_MAXT = 3;  // row tiles per warp in the first column: ceil((nt + 1) / warps) <= 3
+constexpr int FIT_MAXT = 2;  // row tiles per worker warp and column: nt <= 2 NW
 constexpr int NPAD = CNGP_MAX_N + 8;
 // Shared-memory tile pool.  With h = ceil(nt/2): region A holds the packed lower triangle of the top-left h x h tile
 // block while columns k < h are being factored, region B the (nt-h) x h block below it; rows < h are dead once column
@@ -54,16 +66,25 @@ struct FitArgs {
   long long a_col_stride;
 };
 
-// In-warp Cholesky of an 8x8 SPD tile held in the lane layout, followed by the inverse of the factor.  This sits on
-// the critical path of every tile column, so it is built for latency: the tile stays in registers, column k is
-// exchanged with four shuffles per step, the pivot uses rsqrt (sqrt + div cost 165 dependent cycles, rsqrt 80), and
-// the logarithms of the pivots are NOT taken here - the pivots are parked in dpiv and logged in parallel at the end.
-// dt / linv: 64-double shared scratch private to the calling warp.  Returns the failing pivot (1-based) or 0.
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// In-warp Cholesky of an 8x8 SPD tile held in the lane layout, fused with the inverse of the factor.  This is the
+// critical path of every tile column, so it is built for latency: the tile stays in registers, column k is exchanged
+// with independent shuffles, the pivot uses rsqrt (sqrt + div cost 165 dependent cycles, rsqrt 80), and the inverse
+// rides along for free: the row operations of the elimination are applied to an identity tile in the same step
+// (forward substitution L X = I by columns: X[k] = x[k] / L[k][k], x[r] -= L[r][k] X[k]), so there is no second pass.
+// The logarithms of the pivots are NOT taken here - the pivots are parked in dpiv and logged in parallel at the end.
 // On return linv holds inv(L) row-major (zeros above the diagonal) and dpiv[0..7] the diagonal of L.
-__device__ __forceinline__ int chol8_inv8(tile2 c, int lane, double* dt, double* linv, double* dpiv) {
+// Returns the failing pivot (1-based) or 0.
+__device__ __forceinline__ int chol8_inv8(tile2 c, int lane, double* linv, double* dpiv) {
   const int r = lane >> 2, q = lane & 3;
   int fail = 0;
-  double rsv[8];
+  tile2 x{r == 2 * q ? 1.0 : 0.0, r == 2 * q + 1 ? 1.0 : 0.0};
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const double v = (k & 1) ? c.b : c.a;                              // my entry of column pair k>>1
@@ -71,56 +92,39 @@ __device__ __forceinline__ int chol8_inv8(tile2 c, int lane, double* dt, double*
     const double trk = __shfl_sync(0xffffffffu, v, 4 * r + (k >> 1));    // T[r][k]
     const double tc0 = __shfl_sync(0xffffffffu, v, 8 * q + (k >> 1));    // T[2q][k]
     const double tc1 = __shfl_sync(0xffffffffu, v, 8 * q + 4 + (k >> 1));// T[2q+1][k]
+    const double xka = __shfl_sync(0xffffffffu, x.a, 4 * k + q);         // x[k][2q]
+    const double xkb = __shfl_sync(0xffffffffu, x.b, 4 * k + q);         // x[k][2q+1]
     if (!(pk > 0.0) && fail == 0) fail = k + 1;
     const double rs = rsqrt(pk);
-    rsv[k] = rs;
     const double lrk = trk * rs;
     if (2 * q > k && r >= 2 * q) c.a = fma(-lrk, tc0 * rs, c.a);
     if (2 * q + 1 > k && r >= 2 * q + 1) c.b = fma(-lrk, tc1 * rs, c.b);
-    if (2 * q == k && r >= k) c.a = (r == k) ? pk * rs : lrk;
-    if (2 * q + 1 == k && r >= k) c.b = (r == k) ? pk * rs : lrk;
+    const double xsa = xka * rs, xsb = xkb * rs;
+    if (r == k) { x.a = xsa; x.b = xsb; }
+    if (r > k) { x.a = fma(-lrk, xsa, x.a); x.b = fma(-lrk, xsb, x.b); }
+    if (lane == 0) dpiv[k] = pk * rs;
   }
-  tile_store(dt, lane, c);
-  {
-    const int kk = lane & 7, src = 4 * kk + (kk >> 1);   // L[kk][kk] lives in lane (kk, kk/2), element kk & 1
-    const double da = __shfl_sync(0xffffffffu, c.a, src), db = __shfl_sync(0xffffffffu, c.b, src);
-    if (lane < 8) dpiv[lane] = (lane & 1) ? db : da;
-  }
-  __syncwarp();
-  // inverse by columns: lane cc < 8 owns column cc of X = inv(L)
-  if (lane < 8) {
-    const int cc = lane;
-    double xcol[8];
-#pragma unroll
-    for (int rr = 0; rr < 8; ++rr) {
-      double acc = 0.0;
-#pragma unroll
-      for (int m = 0; m < 8; ++m)
-        if (m < rr) acc = fma(dt[rr * 8 + m], (m >= cc) ? xcol[m] : 0.0, acc);
-      const double v = (rr == cc) ? rsv[rr] : -acc * rsv[rr];
-      xcol[rr] = (rr >= cc) ? v : 0.0;
-    }
-#pragma unroll
-    for (int rr = 0; rr < 8; ++rr) linv[rr * 8 + cc] = xcol[rr];
-  }
+  tile_store(linv, lane, x);
   __syncwarp();
   return fail;
 }
 
-template <int KID, int FIT_WARPS>
-__global__ void __launch_bounds__(FIT_WARPS * 32) gp_fit_kernel(const FitArgs a) {
-  constexpr int FIT_THREADS = FIT_WARPS * 32;
+template <int KID, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32) gp_fit_kernel(const FitArgs a) {
+  constexpr int FIT_THREADS = (NW + 1) * 32;
   extern __shared__ __align__(128) double pool[];               // tile pool, see fit_pool_tiles
   __shared__ double fx[NPAD], fxx[NPAD], fc[NPAD], fs[NPAD];   // per-point features
   __shared__ double ys[NPAD];
-  __shared__ double zs[NPAD];
+  __shared__ __align__(16) double zs[NPAD];
   __shared__ LeafConst hc[CNGP_MAX_LEAVES];
   __shared__ KProg kps;
-  __shared__ __align__(16) double dt[64];
-  __shared__ __align__(16) double linv[64];
+  __shared__ __align__(16) double linv[64];      // inv(L_jj) of the current column (diagonal warp -> workers)
+  __shared__ __align__(16) double dpart[64];     // Ky(j+1,j+1) - sum_{k<j} ... (worker 0 -> diagonal warp)
+  __shared__ __align__(16) double etab[128];     // exp_tab tables scaled by the leaf variances
   __shared__ double dpiv[NPAD];          // diagonal of L (pivots), logged in parallel at the end
-  __shared__ double s_red[FIT_WARPS];
+  __shared__ double s_red[NW + 1], s_red2[NW + 1];
   __shared__ int s_fail;
+  __shared__ __align__(16) double zero2[2];
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int r = lane >> 2, q = lane & 3;
@@ -131,9 +135,17 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) gp_fit_kernel(const FitArgs a)
   const double* th = a.theta + ti * a.theta_stride;
   const int N = a.N, nt = a.nt;
   const int h = (nt + 1) / 2, nb = nt - h;          // tile rows of the top block / bottom block
+  const int hh = h * (h + 1) / 2;                   // tiles in region A
   const double noise = (KID == KID_TILES) ? 0.0 : th[a.kp.n_params];
   FastK<KID> fk;
-  if (KID != KID_GENERIC && KID != KID_TILES) fk.init(th);
+  if (KID != KID_GENERIC && KID != KID_TILES) {
+    fk.init(th);
+    if (tid < 64) {
+      const double t = EXP2_TAB64[tid];
+      etab[tid] = fk.scale1() * t;
+      etab[64 + tid] = fk.scale2() * t;
+    }
+  }
 
   for (int i = tid; i < nt * 8; i += FIT_THREADS) {
     const double xv = (KID != KID_TILES && i < N) ? a.x[(long long)win * N + i] : 0.0;
@@ -152,24 +164,41 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) gp_fit_kernel(const FitArgs a)
   }
   __syncthreads();
 
-  // Ky(row, col) from the staged features; identity padding beyond N
-  auto ky_entry = [&](int row, int col, const PointFeat& fa, const PointFeat& fb) -> double {
-    if (KID == KID_TILES) return 0.0;   // never used: the tiles are loaded below
-    if (row < N && col < N) {
-      if (KID == KID_GENERIC) return keval_generic_sym(&kps, hc, fa.x, fb.x, row == col);
-      return fk.eval(fa, fb, row == col);
-    }
-    return (row == col) ? 1.0 : 0.0;
-  };
   auto feat_at = [&](int i) -> PointFeat {
     if (KID == KID_GENERIC) return PointFeat{fx[i], 0.0, 0.0, 0.0};
     if (KID == KID_RBF_PER) return PointFeat{fx[i], fxx[i], fc[i], fs[i]};
     return PointFeat{fx[i], fxx[i], 0.0, 0.0};
   };
+  // Ky(row, col) without the diagonal term; identity padding beyond N
+  auto ky_entry = [&](int row, int col, const PointFeat& fa, const PointFeat& fb) -> double {
+    if (KID == KID_TILES) return 0.0;   // never used: the tiles are loaded
+    if (row < N && col < N) {
+      if (KID == KID_GENERIC) return keval_generic_sym(&kps, hc, fa.x, fb.x, row == col);
+      return fk.eval_tab(fa, fb, row == col, etab);
+    }
+    return (row == col) ? 1.0 : 0.0;
+  };
+  // tile (i, c) of Ky in the lane layout (dadd on the diagonal entries), evaluated or - KID_TILES - loaded
+  auto ky_tile = [&](int i, int c, double dadd) -> tile2 {
+    if (KID == KID_TILES) {
+      const double2 av = *reinterpret_cast<const double2*>(a.Asrc + c * a.a_col_stride + (long long)i * 64 + 2 * lane);
+      return tile2{av.x, av.y};
+    }
+    const int c0 = 8 * c + 2 * q, c1 = c0 + 1, row = 8 * i + r;
+    const PointFeat fr = feat_at(row), f0 = feat_at(c0), f1 = feat_at(c1);
+    double v0 = ky_entry(row, c0, fr, f0), v1 = ky_entry(row, c1, fr, f1);
+    if (row == c0 && row < N) v0 += dadd;
+    if (row == c1 && row < N) v1 += dadd;
+    return tile2{v0, v1};
+  };
+  // pool slot of factor tile (i, k)
+  auto pool_idx = [&](int i, int k) -> int {
+    if (k < h) return (i < h) ? (k * h - k * (k - 1) / 2 + i - k) : (hh + k * nb + i - h);
+    return (k - h) * nb - (k - h) * (k - h - 1) / 2 + i - k;
+  };
 
   double* Lp = a.L + lp * (long long)tiles_in_lower(nt) * 64;
-  double* poolA = pool + 2 * lane;                       // lane-offset views of the two pool regions
-  double* poolB = pool + (h * (h + 1) / 2) * 64 + 2 * lane;
+  double* poolL = pool + 2 * lane;                       // lane-offset view of the pool
   const int max_attempts = (a.jitter_retry && KID != KID_TILES) ? 6 : 1;
   double extra = 0.0;
   int fail_pivot = 0, attempts_used = 0;
@@ -186,140 +215,177 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) gp_fit_kernel(const FitArgs a)
       if (lane == 0) s_red[w] = s;
       __syncthreads();
       s = 0.0;
-      for (int i = 0; i < FIT_WARPS; ++i) s += s_red[i];
+      for (int i = 0; i <= NW; ++i) s += s_red[i];
       extra = s / N * 1e-6;
     } else if (attempt > 1) {
       extra *= 10.0;
     }
-    if (tid == 0) s_fail = 0;
+    if (tid == 0) { s_fail = 0; zero2[0] = 0.0; zero2[1] = 0.0; }
     __syncthreads();
     const double dadd = noise + CNGP_JITTER + extra;
 
-    for (int j = 0; j < nt; ++j) {
-      // my row tiles of this column: i_t = j + w + FIT_WARPS t  (t < nvalid), plus possibly the z row (i == nt)
-      const int rem = nt - j - w;                       // i_t < nt  <=>  FIT_WARPS t < rem
-      const int nvalid = rem > 0 ? min(FIT_MAXT, (rem + FIT_WARPS - 1) / FIT_WARPS) : 0;
-      const bool zmine = rem >= 0 && (rem % FIT_WARPS) == 0 && (rem / FIT_WARPS) < FIT_MAXT;
-      // ---- left-looking update: S_t = sum_{k<j} L(i_t,k) L(j,k)^T, every tile read from the shared-memory pool
-      tile2 S[FIT_MAXT];
-      const double* xb[FIT_MAXT];    // per-tile base: region + i_t * 64 (the column part is added per k)
-      bool inA[FIT_MAXT];
+    if (w == NW) {
+      // ================= diagonal warp =================
+      tile2 Cd = ky_tile(0, 0, dadd);
+      for (int j = 0; j < nt; ++j) {
+        const int f = chol8_inv8(Cd, lane, linv, dpiv + 8 * j);
+        if (lane == 0 && f && s_fail == 0) s_fail = 8 * j + f;
+        named_bar_arrive(1, FIT_THREADS);                           // inv(L_jj) is in linv
+        tile_store(Lp + (long long)tile_index(j, j, nt) * 64, lane, tile_load(linv, lane));
+        named_bar_sync(2, FIT_THREADS);                             // column j stored, dpart of column j+1 parked
+        if (j + 1 < nt) {
+          const tile2 Y = tile_load(pool + pool_idx(j + 1, j) * 64, lane);
+          tile2 S = tile_load(dpart, lane);
+          tile_mma(S, tile2{-Y.a, -Y.b}, Y);
+          Cd = S;
+        }
+      }
+    } else {
+      // ================= worker warps =================
+      // Slot t of this warp in column c is row tile i = c + w + NW t:  i == c the diagonal tile (worker 0 only
+      // pre-accumulates it for the diagonal warp), c < i < nt a regular tile, i == nt the z row (y carried as an extra
+      // 1-row tile row under the matrix).  Column 0 has nt + 1 rows for 2 NW slots, so its z row sits in the slot of
+      // the diagonal tile (0,0), which the diagonal warp evaluates itself.
+      auto slot_kind = [&](int c, int t) -> int {   // 0 none, 1 regular, 2 z row, 3 diagonal
+        const int i = c + w + NW * t;
+        if (c == 0 && w == 0 && t == 0) return 2;
+        if (i == c) return 3;
+        if (i < nt) return 1;
+        return (i == nt && c > 0) ? 2 : 0;
+      };
+      auto y_tile = [&](int c) -> tile2 {
+        return tile2{r == 0 ? ys[8 * c + 2 * q] : 0.0, r == 0 ? ys[8 * c + 2 * q + 1] : 0.0};
+      };
+      // z-row operand as a tile: row 0 = z[8k .. 8k+7], rows 1..7 = 0  (lanes r > 0 read a zero word with stride 0)
+      const double* zbase = (r == 0) ? zs + 2 * q : zero2;
+      const int zstride = (r == 0) ? 8 : 0;
+
+      tile2 Ccur[FIT_MAXT];
 #pragma unroll
       for (int t = 0; t < FIT_MAXT; ++t) {
-        S[t] = tile2{0.0, 0.0};
-        const int i = j + w + FIT_WARPS * t;
-        inA[t] = (j < h) && (i < h);
-        xb[t] = (inA[t] ? poolA : poolB) + i * 64;
+        const int kd = slot_kind(0, t);
+        Ccur[t] = kd == 1 ? ky_tile(w + NW * t, 0, dadd) : (kd == 2 ? y_tile(0) : tile2{0.0, 0.0});
       }
-      tile2 Sz{0.0, 0.0};
-      const int kA_end = j < h ? j : h;
-      {
-        // columns k < h:  A-tile (i,k) at A[k h - k(k-1)/2 + i - k],  B-tile (i,k) at B[k nb + i - h]
-        int offA = 0, offB = -h;
-        const double* yb = (j < h ? poolA : poolB) + j * 64;
-        const bool yA = j < h;
-#pragma unroll 2
-        for (int k = 0; k < kA_end; ++k) {
-          const double2 yv = *reinterpret_cast<const double2*>(yb + (yA ? offA : offB) * 64);
-          const tile2 Y{yv.x, yv.y};
-#pragma unroll
-          for (int t = 0; t < FIT_MAXT; ++t) {
-            if (t < nvalid) {
-              const double2 xv = *reinterpret_cast<const double2*>(xb[t] + (inA[t] ? offA : offB) * 64);
-              tile_mma(S[t], tile2{xv.x, xv.y}, Y);
-            }
-          }
-          if (zmine) {
-            tile2 X{0.0, 0.0};
-            if (r == 0) { X.a = zs[8 * k + 2 * q]; X.b = zs[8 * k + 2 * q + 1]; }
-            tile_mma(Sz, X, Y);
-          }
-          offA += h - k - 1;
-          offB += nb;
-        }
-      }
-      if (j > h) {
-        // columns h <= k < j live in region A again: tile (i,k) at A[(k-h) nb - (k-h)(k-h-1)/2 + i - k]
-        int off2 = -h;
-        const double* yb = poolA + j * 64;
-#pragma unroll 2
-        for (int k = h; k < j; ++k) {
-          const double2 yv = *reinterpret_cast<const double2*>(yb + off2 * 64);
-          const tile2 Y{yv.x, yv.y};
-#pragma unroll
-          for (int t = 0; t < FIT_MAXT; ++t) {
-            if (t < nvalid) {
-              const double2 xv = *reinterpret_cast<const double2*>(poolA + (off2 + j + w + FIT_WARPS * t) * 64);
-              tile_mma(S[t], tile2{xv.x, xv.y}, Y);
-            }
-          }
-          if (zmine) {
-            tile2 X{0.0, 0.0};
-            if (r == 0) { X.a = zs[8 * k + 2 * q]; X.b = zs[8 * k + 2 * q + 1]; }
-            tile_mma(Sz, X, Y);
-          }
-          off2 += nb - (k - h) - 1;
-        }
-      }
-      // ---- C_t = Ky tile - S_t (Ky evaluated here, never stored) ----
-      {
-        const int c0 = 8 * j + 2 * q, c1 = c0 + 1;
-        const PointFeat fc0 = feat_at(c0), fc1 = feat_at(c1);
+
+      for (int j = 0; j < nt; ++j) {
+        const int c = j + 1;
+        // ---- (b) look-ahead: partial sums of column c over k < j, Ky tiles of column c ----
+        tile2 S0[FIT_MAXT], S1[FIT_MAXT], Kn[FIT_MAXT];
+        int kind[FIT_MAXT];
 #pragma unroll
         for (int t = 0; t < FIT_MAXT; ++t) {
-          if (t < nvalid) {
-            const int row = 8 * (j + w + FIT_WARPS * t) + r;
-            double v0, v1;
-            if (KID == KID_TILES) {
-              const double2 av = *reinterpret_cast<const double2*>(
-                  a.Asrc + j * a.a_col_stride + (long long)(j + w + FIT_WARPS * t) * 64 + 2 * lane);
-              v0 = av.x; v1 = av.y;
-            } else {
-              const PointFeat fr = feat_at(row);
-              v0 = ky_entry(row, c0, fr, fc0); v1 = ky_entry(row, c1, fr, fc1);
-              if (row == c0 && row < N) v0 += dadd;
-              if (row == c1 && row < N) v1 += dadd;
+          kind[t] = c < nt ? slot_kind(c, t) : 0;
+          S0[t] = tile2{0.0, 0.0};
+          S1[t] = tile2{0.0, 0.0};
+          Kn[t] = tile2{0.0, 0.0};
+        }
+        if (kind[0] != 0) {
+          // One loop serves both pool regions and the z row: every operand is (pointer, stride, stride decrement) -
+          // region A columns shrink by one tile per k, region B columns have a fixed pitch, the z operand strides 8.
+          auto accumulate = [&](int k0, int k1, const double* pY, int sY, int dY, const double* pX0, int sX0, int dX0,
+                                const double* pX1, int sX1, int dX1, const bool two) {
+            if (k0 >= k1) return;
+            tile2 Y = tile_load(pY, 0), X0 = tile_load(pX0, 0), X1{0.0, 0.0};
+            if (two) X1 = tile_load(pX1, 0);
+            for (int k = k0; k < k1; k += 2) {
+              pY += sY; sY -= dY; pX0 += sX0; sX0 -= dX0; pX1 += sX1; sX1 -= dX1;
+              tile2 Yn{0.0, 0.0}, X0n{0.0, 0.0}, X1n{0.0, 0.0};
+              if (k + 1 < k1) {
+                Yn = tile_load(pY, 0); X0n = tile_load(pX0, 0);
+                if (two) X1n = tile_load(pX1, 0);
+              }
+              tile_mma(S0[0], X0, Y);
+              if (two) tile_mma(S0[1], X1, Y);
+              if (k + 1 >= k1) break;
+              pY += sY; sY -= dY; pX0 += sX0; sX0 -= dX0; pX1 += sX1; sX1 -= dX1;
+              if (k + 2 < k1) {
+                Y = tile_load(pY, 0); X0 = tile_load(pX0, 0);
+                if (two) X1 = tile_load(pX1, 0);
+              }
+              tile_mma(S1[0], X0n, Yn);
+              if (two) tile_mma(S1[1], X1n, Yn);
             }
-            S[t].a = v0 - S[t].a;
-            S[t].b = v1 - S[t].b;
+          };
+          const bool two = kind[1] != 0;
+          const int k1 = j < h ? j : h;
+          // columns k < min(j, h): tile (i,k) at A[k(h-1) - k(k-1)/2 + i] for i < h, at B[k nb + i - h] otherwise
+          {
+            const double* pA = poolL;
+            const double* pB = poolL + (hh - h) * 64;
+            const bool yA = c < h;
+            const double* pX[FIT_MAXT]; int sX[FIT_MAXT], dX[FIT_MAXT];
+#pragma unroll
+            for (int t = 0; t < FIT_MAXT; ++t) {
+              const int i = c + w + NW * t;
+              const bool xa = i < h;
+              pX[t] = kind[t] == 2 ? zbase : (xa ? pA : pB) + i * 64;
+              sX[t] = kind[t] == 2 ? zstride : (xa ? (h - 1) * 64 : nb * 64);
+              dX[t] = (kind[t] != 2 && xa) ? 64 : 0;
+            }
+            accumulate(0, k1, (yA ? pA : pB) + c * 64, yA ? (h - 1) * 64 : nb * 64, yA ? 64 : 0, pX[0], sX[0], dX[0],
+                       pX[1], sX[1], dX[1], two);
+          }
+          // columns h <= k < j live in region A again: tile (i,k) at A[(k-h) nb - (k-h)(k-h-1)/2 + i - k]
+          if (j > h) {
+            const double* p2 = poolL - h * 64;
+            const double* pX[FIT_MAXT]; int sX[FIT_MAXT], dX[FIT_MAXT];
+#pragma unroll
+            for (int t = 0; t < FIT_MAXT; ++t) {
+              const int i = c + w + NW * t;
+              pX[t] = kind[t] == 2 ? zbase + zstride * h : p2 + i * 64;
+              sX[t] = kind[t] == 2 ? zstride : (nb - 1) * 64;
+              dX[t] = kind[t] == 2 ? 0 : 64;
+            }
+            accumulate(h, j, p2 + c * 64, (nb - 1) * 64, 64, pX[0], sX[0], dX[0], pX[1], sX[1], dX[1], two);
+          }
+          // Ky tiles of column c (never stored); the diagonal row's partial result goes to the diagonal warp
+#pragma unroll
+          for (int t = 0; t < FIT_MAXT; ++t) {
+            if (kind[t] != 0) {
+              S0[t].a += S1[t].a; S0[t].b += S1[t].b;
+              Kn[t] = kind[t] == 2 ? y_tile(c) : ky_tile(c + w + NW * t, c, dadd);
+            }
+          }
+          if (kind[0] == 3) tile_store(dpart, lane, tile2{Kn[0].a - S0[0].a, Kn[0].b - S0[0].b});
+        }
+        named_bar_sync(1, FIT_THREADS);                             // inv(L_jj) published
+        // ---- (d) rows below the diagonal: L(i,j) = C(i,j) inv(L_jj)^T -> pool and global; z_j ----
+        {
+          const tile2 Yinv = tile_load(linv, lane);
+          double* colj = Lp + (long long)tile_index(j, j, nt) * 64;
+#pragma unroll
+          for (int t = 0; t < FIT_MAXT; ++t) {
+            const int kd = slot_kind(j, t);
+            if (kd == 1 || kd == 2) {
+              const int i = j + w + NW * t;
+              tile2 Lt{0.0, 0.0};
+              tile_mma(Lt, Ccur[t], Yinv);
+              if (kd == 1) {
+                tile_store(pool + pool_idx(i, j) * 64, lane, Lt);
+                tile_store(colj + (i - j) * 64, lane, Lt);
+              } else if (r == 0) {
+                zs[8 * j + 2 * q] = Lt.a; zs[8 * j + 2 * q + 1] = Lt.b;
+              }
+            }
           }
         }
-        if (zmine) {
-          Sz.a = ((r == 0) ? ys[c0] : 0.0) - Sz.a;
-          Sz.b = ((r == 0) ? ys[c1] : 0.0) - Sz.b;
-        }
-      }
-      // ---- diagonal tile: factor + invert (warp 0 owns i == j at t == 0) ----
-      double* colj = Lp + (long long)tile_index(j, j, nt) * 64;
-      if (w == 0) {
-        const int f = chol8_inv8(S[0], lane, dt, linv, dpiv + 8 * j);
-        if (lane == 0 && f && s_fail == 0) s_fail = 8 * j + f;
-        tile_store(colj, lane, tile_load(linv, lane));
-      }
-      __syncthreads();
-      // ---- rows below: L(i,j) = C_t inv(L_jj)^T  -> pool (for later columns) and global (for phase B) ----
-      const tile2 Yinv = tile_load(linv, lane);
-      // pool position of tile (i, j): same mapping as above with k = j
-      const int pj = j < h ? (j * h - j * (j - 1) / 2 - j) : ((j - h) * nb - (j - h) * (j - h - 1) / 2 - j);
-      const int pjB = j * nb - h;
+        named_bar_sync(2, FIT_THREADS);
+        // ---- (a) finish column c with the k = j term ----
+        if (kind[0] != 0) {
+          const tile2 Y = tile_load(pool + pool_idx(c, j) * 64, lane);
 #pragma unroll
-      for (int t = 0; t < FIT_MAXT; ++t) {
-        if (t < nvalid && (w + t) > 0) {
-          const int i = j + w + FIT_WARPS * t;
-          tile2 Lt{0.0, 0.0};
-          tile_mma(Lt, S[t], Yinv);
-          tile_store(colj + (i - j) * 64, lane, Lt);
-          double* dst = (j < h && i >= h) ? (poolB + (pjB + i) * 64) : (poolA + (pj + i) * 64);
-          *reinterpret_cast<double2*>(dst) = make_double2(Lt.a, Lt.b);
+          for (int t = 0; t < FIT_MAXT; ++t) {
+            if (kind[t] == 1 || kind[t] == 2) {
+              const int i = c + w + NW * t;
+              const tile2 X = kind[t] == 2 ? tile_load(zbase + zstride * j, 0) : tile_load(pool + pool_idx(i, j) * 64, lane);
+              tile_mma(S0[t], X, Y);
+              Ccur[t] = tile2{Kn[t].a - S0[t].a, Kn[t].b - S0[t].b};
+            }
+          }
         }
       }
-      if (zmine) {
-        tile2 Lt{0.0, 0.0};
-        tile_mma(Lt, Sz, Yinv);
-        if (r == 0) { zs[8 * j + 2 * q] = Lt.a; zs[8 * j + 2 * q + 1] = Lt.b; }
-      }
-      __syncthreads();
     }
+    __syncthreads();
     fail_pivot = s_fail;
     attempts_used = attempt;
     if (fail_pivot == 0) break;
@@ -339,12 +405,11 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) gp_fit_kernel(const FitArgs a)
     qs += __shfl_xor_sync(0xffffffffu, qs, o);
     hl += __shfl_xor_sync(0xffffffffu, hl, o);
   }
-  __syncthreads();
-  if (lane == 0) { s_red[w] = qs; fx[w] = hl; }   // fx is free by now
+  if (lane == 0) { s_red[w] = qs; s_red2[w] = hl; }
   __syncthreads();
   if (tid == 0) {
     double quad = 0.0, hls = 0.0;
-    for (int i = 0; i < FIT_WARPS; ++i) { quad += s_red[i]; hls += fx[i]; }
+    for (int i = 0; i <= NW; ++i) { quad += s_red[i]; hls += s_red2[i]; }
     const double logdet = 2.0 * hls;
     const double nanv = __longlong_as_double(0x7ff8000000000000LL);
     const bool bad = fail_pivot != 0;

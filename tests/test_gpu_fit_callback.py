@@ -51,8 +51,12 @@ def test_optimize_reaches_scipy_optimum_on_slipval(gp_ctx, slipval, kname):
     e = go.KernelExpr(kname)
     th_ref, noise_ref, lml_ref, nev_ref = go.optimize(e, xtr, ytr)
     assert np.all(theta > 0) and nfev[0] <= 1000
-    assert lml[0] >= lml_ref - 1e-6 * abs(lml_ref)
-    assert abs(lml[0] - lml_ref) < 1e-4 * abs(lml_ref)
+    # Optimiser trajectories are not reproducible to 1e-9 across implementations: the fitted
+    # optimum is compared through the LML it reaches - at least the oracle's; on a multimodal surface (periodic
+    # leaf) a 1e-16 difference in the first evaluations may legitimately end in a better local optimum.
+    assert lml[0] >= lml_ref - 1e-6 * abs(lml_ref), (lml[0], lml_ref)
+    if "periodic" not in kname:
+        assert abs(lml[0] - lml_ref) < 1e-4 * abs(lml_ref), (lml[0], lml_ref)
     # the reported LML is the oracle's LML at the returned hyper-parameters
     assert rel(lml[0], go.inference(e, theta[0, :-1], theta[0, -1], xtr, ytr).lml) < TOL
 
