@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU-box round: parity tests, smoke, bench, ncu launch list, ncu full captures of the two predict kernels.
+# One GPU-box round: parity tests, smoke, bench, ncu launch list, ncu full captures (CSV exports) of the two predict kernels, large-window bench.
 # usage (under gpurun): bash tools/gpu_round.sh [tag]
 TAG=${1:-r01}
 O=gpurun_out
@@ -10,8 +10,7 @@ timeout 300 python __graft_entry__.py --smoke > $O/smoke_$TAG.log 2>&1; echo "sm
 timeout 900 python bench.py --steps 10 --warmup 3 > $O/bench_$TAG.json 2> $O/bench_$TAG.err; echo "bench rc=$?" >> $O/bench_$TAG.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_under_ncu_$TAG.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gp_var -s 1 -c 1 -f -o $O/prof_var_$TAG \
-    python tools/prof_predict.py 4096 256 600 1 > $O/ncu_var_$TAG.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gp_fit -s 1 -c 1 -f -o $O/prof_fit_$TAG \
-    python tools/prof_predict.py 4096 256 600 1 > $O/ncu_fit_$TAG.log 2>&1
+bash tools/ncu_capture.sh var_$TAG gp_var python tools/prof_predict.py 4096 256 600 1 > /dev/null 2>&1
+bash tools/ncu_capture.sh fit_$TAG gp_fit python tools/prof_predict.py 4096 256 600 1 > /dev/null 2>&1
+timeout 600 python tools/bench_large.py 32768 3 > $O/bench_large_$TAG.json 2> $O/bench_large_$TAG.err
 tail -3 $O/pytest_gpu_$TAG.log; tail -2 $O/smoke_$TAG.log; cat $O/bench_$TAG.json | cut -c1-1500; tail -2 $O/bench_$TAG.err
