@@ -505,10 +505,10 @@ extern "C" int cngp_large_factor_panel(cngp_ctx* ctx, const cngp_large_plan* p, 
   fa.status = status + k; fa.jitter_retry = 0;
   fa.Asrc = Acol + rdiag * 64; fa.a_col_stride = cstride;
   // logdet / status are indexed by the kernel with the problem id p = problem0 + blockIdx.x = 0
-  const size_t smem = fit_smem_bytes(LG_BT);
-  LCU(ctx, cudaFuncSetAttribute(gp_fit_kernel<KID_TILES, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = fit_smem_bytes(LG_BT, FIT_NW_FULL * FIT_T_FULL);
+  LCU(ctx, cudaFuncSetAttribute(gp_fit_kernel<KID_TILES, FIT_NW_FULL, FIT_T_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
-  gp_fit_kernel<KID_TILES, 16><<<1, 17 * 32, smem, s>>>(fa);   // 16 workers + the diagonal warp
+  gp_fit_kernel<KID_TILES, FIT_NW_FULL, FIT_T_FULL><<<1, (FIT_NW_FULL + 1) * 32, smem, s>>>(fa);   // workers + the diagonal warp
   cngp_ctx_end(ctx);
   // 2. inverse of the block factor
   cngp_ctx_begin(ctx, CNGP_PROF_LARGE);

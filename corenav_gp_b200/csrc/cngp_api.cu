@@ -415,18 +415,18 @@ static int launch_var(cngp_ctx* ctx, int kid, VarArgs& va, long long nwin, cudaS
     default: return launch_var_k<NT_MAX, G, WG, NSLOT, CT, KID_GENERIC>(ctx, va, nwin, s);
   }
 }
-template <int KID, int WARPS>
+template <int KID, int NW, int T>
 static void launch_fit_k(const FitArgs& fa, long long nprob, cudaStream_t s) {
-  const size_t smem = fit_smem_bytes(fa.nt);
-  cudaFuncSetAttribute(gp_fit_kernel<KID, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  gp_fit_kernel<KID, WARPS><<<(unsigned)nprob, (WARPS + 1) * 32, smem, s>>>(fa);   // WARPS workers + the diagonal warp
+  const size_t smem = fit_smem_bytes(fa.nt, NW * T);
+  cudaFuncSetAttribute(gp_fit_kernel<KID, NW, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  gp_fit_kernel<KID, NW, T><<<(unsigned)nprob, (NW + 1) * 32, smem, s>>>(fa);   // NW workers + the diagonal warp
 }
 template <int KID>
 static void launch_fit_w(const FitArgs& fa, long long nprob, cudaStream_t s) {
-  // row tiles per column (nt) must fit WARPS * FIT_MAXT
-  if (fa.nt <= 4 * FIT_MAXT) launch_fit_k<KID, 4>(fa, nprob, s);
-  else if (fa.nt <= 8 * FIT_MAXT) launch_fit_k<KID, 8>(fa, nprob, s);
-  else launch_fit_k<KID, 16>(fa, nprob, s);
+  // row tiles (nt) must fit NW workers x T slots
+  if (fa.nt <= 8) launch_fit_k<KID, 4, 2>(fa, nprob, s);
+  else if (fa.nt <= 16) launch_fit_k<KID, 8, 2>(fa, nprob, s);
+  else launch_fit_k<KID, FIT_NW_FULL, FIT_T_FULL>(fa, nprob, s);
 }
 static void launch_fit(int kid, const FitArgs& fa, long long nprob, cudaStream_t s) {
   switch (kid) {

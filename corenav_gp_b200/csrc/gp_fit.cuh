@@ -11,6 +11,9 @@
 // Row tiles are OWNED: row i belongs to worker i % NW for the whole factorisation (slot t = i / NW of that warp), so a
 // worker's tiles of the current column, of the next column and the factor tiles it has just produced all stay in
 // registers under compile-time indices, and the k = j term of the look-ahead needs one operand from shared memory only.
+// (Measured alternatives, tools/fit_bench.cu: dedicated evaluator warps staging Ky ahead of the factorisation lose -
+// their scalar FP64 work crawls behind the workers' DMMA on the shared FP64 pipe - and so does moving the diagonal warp
+// to a sub-partition of its own; evaluating in a phase of its own, all workers at once, is what the pipe likes.)
 //
 //   workers, step j:  (b) S(i, j+1) = sum_{k<j} L(i,k) L(j+1,k)^T for their rows i >= j+1 (one pass over the tile pool:
 //                         1 + A 16-byte loads and 2A DMMA per k for A live rows), evaluate Ky(i, j+1) (the kernel
@@ -33,6 +36,7 @@
 namespace cngp {
 
 constexpr int NPAD = CNGP_MAX_N + 8;
+constexpr int FIT_NW_FULL = 11, FIT_T_FULL = 3;   // workers x row-tile slots for nt > 16 (CNGP_MAX_N = 256: nt <= 32)
 // Shared-memory tile pool.  With h = ceil(nt/2): columns k < h are packed one after the other, column k holding its
 // rows k..nt-1 (tile (i,k) at cb(k) + i - k, cb(k) = k nt - k(k-1)/2).  Rows < h are dead once column h starts, so
 // column k = h + m re-uses the dead head of column m (h - m >= nt - k tiles): tile (i,k) at cb(m) + i - k.  Walking k
@@ -71,7 +75,16 @@ struct FitArgs {
   // evaluated - tile (i, j) of the block at Asrc + j * a_col_stride + i * 64 (lower tiles only are read).
   const double* Asrc;
   long long a_col_stride;
+#ifdef CNGP_FIT_TIMING
+  long long* dbg;        // tools/fit_bench.cu: per-warp phase cycle counters of block 0, [warp][8]
+#endif
 };
+
+#ifdef CNGP_FIT_TIMING
+#define FIT_STAMP(ph) do { const long long now_ = clock64(); t_acc[ph] += now_ - t_last; t_last = now_; } while (0)
+#else
+#define FIT_STAMP(ph) do { } while (0)
+#endif
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -116,3 +129,327 @@ __device__ __forceinline__ int chol8_inv8(tile2 c, int lane, double* linv, doubl
   return fail;
 }
 
+
+template <int N> struct FitIC { static constexpr int value = N; };
+
+// NW workers, T row-tile slots per worker: nt <= NW * T.
+template <int KID, int NW, int T>
+__global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_kernel(const FitArgs a) {
+  constexpr int FIT_THREADS = (NW + 1) * 32;
+  extern __shared__ __align__(128) double pool[];               // tile pool, see fit_pool_tiles
+  __shared__ double fx[NPAD], fxx[NPAD], fc[NPAD], fs[NPAD];   // per-point features
+  __shared__ double ys[NPAD];
+  __shared__ __align__(16) double zs[NPAD];
+  __shared__ LeafConst hc[CNGP_MAX_LEAVES];
+  __shared__ KProg kps;
+  __shared__ __align__(16) double linv[64];      // inv(L_jj) of the current column (diagonal warp -> workers)
+  __shared__ __align__(16) double dpart[2][64];  // Ky(c,c) - sum_{k<c-1} ... of column c, buffer c & 1 (owner -> diagonal warp)
+  __shared__ __align__(16) double etab[128];     // exp_tab tables scaled by the leaf variances
+  __shared__ double dpiv[NPAD];          // diagonal of L (pivots), logged in parallel at the end
+  __shared__ double s_red[NW + 1], s_red2[NW + 1];
+  __shared__ int s_fail;
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int r = lane >> 2, q = lane & 3;
+  const long long lp = blockIdx.x;                 // problem within this launch
+  const long long p = a.problem0 + lp;             // global problem
+  const int win = a.win_map ? a.win_map[p] : (int)(p % a.n_windows);
+  const long long ti = a.theta_mode == 0 ? 0 : (a.theta_mode == 1 ? (long long)win : (a.theta_mode == 3 ? p : p / a.n_windows));
+  const double* th = a.theta + ti * a.theta_stride;
+  const int N = a.N, nt = a.nt;
+  const int h = (nt + 1) / 2;                       // columns >= h re-use the dead heads of columns < h
+  const double noise = (KID == KID_TILES) ? 0.0 : th[a.kp.n_params];
+  FastK<KID> fk;
+  if (KID != KID_GENERIC && KID != KID_TILES) {
+    fk.init(th);
+    if (tid < 64) {
+      const double t = EXP2_TAB64[tid];
+      etab[tid] = fk.scale1() * t;
+      etab[64 + tid] = fk.scale2() * t;
+    }
+  }
+
+  for (int i = tid; i < nt * 8; i += FIT_THREADS) {
+    const double xv = (KID != KID_TILES && i < N) ? a.x[(long long)win * N + i] : 0.0;
+    ys[i] = (KID != KID_TILES && i < N) ? a.y[(long long)win * N + i] : 0.0;
+    PointFeat f{xv, __dmul_rn(xv, xv), 0.0, 0.0};
+    if (KID != KID_GENERIC && KID != KID_TILES) f = fk.point(xv);
+    fx[i] = f.x; fxx[i] = f.xx; fc[i] = f.c; fs[i] = f.s;
+    if (a.feat) {
+      double* fp = a.feat + lp * (long long)(4 * nt * 8);
+      fp[i] = f.x; fp[nt * 8 + i] = f.xx; fp[2 * nt * 8 + i] = f.c; fp[3 * nt * 8 + i] = f.s;
+    }
+  }
+  if (KID == KID_GENERIC) {
+    if (tid < a.kp.n_leaves) hc[tid] = leaf_prepare(a.kp.leaf_type[tid], th + a.kp.leaf_param[tid]);
+    if (tid == 0) kps = a.kp;
+  }
+  __syncthreads();
+
+  auto feat_at = [&](int i) -> PointFeat {
+    if (KID == KID_GENERIC) return PointFeat{fx[i], 0.0, 0.0, 0.0};
+    if (KID == KID_RBF_PER) return PointFeat{fx[i], fxx[i], fc[i], fs[i]};
+    return PointFeat{fx[i], fxx[i], 0.0, 0.0};
+  };
+  // Ky(row, col) without the diagonal term; identity padding beyond N
+  auto ky_entry = [&](int row, int col, const PointFeat& fa, const PointFeat& fb) -> double {
+    if (KID == KID_TILES) return 0.0;   // never used: the tiles are loaded
+    if (row < N && col < N) {
+      if (KID == KID_GENERIC) return keval_generic_sym(&kps, hc, fa.x, fb.x, row == col);
+      return fk.eval_tab(fa, fb, row == col, etab);
+    }
+    return (row == col) ? 1.0 : 0.0;
+  };
+  // tile (i, c) of Ky in the lane layout (dadd on the diagonal entries), evaluated or - KID_TILES - loaded
+  auto ky_tile = [&](int i, int c, double dadd) -> tile2 {
+    if (KID == KID_TILES) {
+      const double2 av = *reinterpret_cast<const double2*>(a.Asrc + c * a.a_col_stride + (long long)i * 64 + 2 * lane);
+      return tile2{av.x, av.y};
+    }
+    const int c0 = 8 * c + 2 * q, c1 = c0 + 1, row = 8 * i + r;
+    const PointFeat fr = feat_at(row), f0 = feat_at(c0), f1 = feat_at(c1);
+    double v0 = ky_entry(row, c0, fr, f0), v1 = ky_entry(row, c1, fr, f1);
+    if (row == c0 && row < N) v0 += dadd;
+    if (row == c1 && row < N) v1 += dadd;
+    return tile2{v0, v1};
+  };
+  // pool slot of factor tile (i, k)
+  auto pool_idx = [&](int i, int k) -> int {
+    const int m = k < h ? k : k - h;
+    return m * nt - m * (m - 1) / 2 + i - k;
+  };
+
+  double* Lp = a.L + lp * (long long)tiles_in_lower(nt) * 64;
+  double* poolL = pool + 2 * lane;                       // lane-offset view of the pool
+  const int max_attempts = (a.jitter_retry && KID != KID_TILES) ? 6 : 1;
+  double extra = 0.0;
+  int fail_pivot = 0, attempts_used = 0;
+
+  for (int attempt = 0; attempt < max_attempts; ++attempt) {
+    if (attempt == 1) {
+      // GPy jitchol: jitter = mean(diag(Ky)) * 1e-6, then x10 per retry
+      double s = 0.0;
+      for (int i = tid; i < N; i += FIT_THREADS) {
+        const PointFeat f = feat_at(i);
+        s += ky_entry(i, i, f, f) + noise + CNGP_JITTER;
+      }
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) s_red[w] = s;
+      __syncthreads();
+      s = 0.0;
+      for (int i = 0; i <= NW; ++i) s += s_red[i];
+      extra = s / N * 1e-6;
+    } else if (attempt > 1) {
+      extra *= 10.0;
+    }
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+    const double dadd = noise + CNGP_JITTER + extra;
+#ifdef CNGP_FIT_TIMING
+    long long t_acc[6] = {0, 0, 0, 0, 0, 0};
+    long long t_last = clock64();
+#endif
+
+    if (w == NW) {
+      // ================= diagonal warp =================
+      tile2 Cd = ky_tile(0, 0, dadd);
+      for (int j = 0; j < nt; ++j) {
+        const int f = chol8_inv8(Cd, lane, linv, dpiv + 8 * j);
+        if (lane == 0 && f && s_fail == 0) s_fail = 8 * j + f;
+        FIT_STAMP(0);
+        named_bar_arrive(1, FIT_THREADS);                           // inv(L_jj) is in linv
+        tile_store(Lp + (long long)tile_index(j, j, nt) * 64, lane, tile_load(linv, lane));
+        named_bar_sync(2, FIT_THREADS);                             // column j stored, dpart of column j+1 parked
+        FIT_STAMP(1);
+        if (j + 1 < nt) {
+          const tile2 Y = tile_load(pool + pool_idx(j + 1, j) * 64, lane);
+          tile2 S = tile_load(dpart[(j + 1) & 1], lane);
+          tile_mma(S, tile2{-Y.a, -Y.b}, Y);
+          Cd = S;
+        }
+        FIT_STAMP(2);
+      }
+    } else {
+      // ================= worker warps =================
+      // slot t of this warp is row tile i = w + NW t, for every column
+      tile2 Ccur[T], Lt[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int i = w + NW * t;
+        Ccur[t] = (i >= 1 && i < nt) ? ky_tile(i, 0, dadd) : tile2{0.0, 0.0};   // (0,0) is the diagonal warp's
+        Lt[t] = tile2{0.0, 0.0};
+      }
+      double za = 0.0, zb = 0.0;    // sum_k L(c,k) z_k in the lane layout, for the next diagonal row c this warp owns
+
+      for (int j = 0; j < nt; ++j) {
+        const int c = j + 1;
+        // ---- (b) look-ahead: partial sums of column c over k < j, Ky tiles of column c ----
+        const int t0 = c > w ? (c - w + NW - 1) / NW : 0;     // first slot with a row >= c
+        const bool own_diag = t0 < T && w + NW * t0 == c && c < nt;
+        tile2 S0[T], S1[T], Kn[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          S0[t] = tile2{0.0, 0.0};
+          S1[t] = tile2{0.0, 0.0};
+          Kn[t] = tile2{0.0, 0.0};
+        }
+        if (c < nt && w + NW * t0 < nt && t0 < T) {
+          // pool pass over slots T0..T-1 (compile-time T0): Y = (c,k) and X_t = (i_t,k) sit in the same pool column.
+          // Slots whose row is beyond nt-1 read (and never use) whatever follows the column - see fit_smem_bytes.
+          auto pass = [&](auto t0c, int k0, int k1, const double* pY) {
+            constexpr int T0 = decltype(t0c)::value;
+            if (k0 >= k1) return;
+            const double* pX = pY + (w - c) * 64;
+            int pitch = (nt - 1) * 64;
+            const double* zp = zs + 8 * k0 + 2 * q;
+            tile2 Y = tile_load(pY, 0), X[T], Yn{0.0, 0.0}, Xn[T];
+#pragma unroll
+            for (int t = T0; t < T; ++t) X[t] = tile_load(pX + t * NW * 64, 0);
+            for (int k = k0; k < k1; k += 2) {
+              pY += pitch; pX += pitch; pitch -= 64;
+              if (k + 1 < k1) {
+                Yn = tile_load(pY, 0);
+#pragma unroll
+                for (int t = T0; t < T; ++t) Xn[t] = tile_load(pX + t * NW * 64, 0);
+              }
+#pragma unroll
+              for (int t = T0; t < T; ++t) dmma884(S0[t].a, S0[t].b, X[t].a, Y.a);
+#pragma unroll
+              for (int t = T0; t < T; ++t) dmma884(S0[t].a, S0[t].b, X[t].b, Y.b);
+              if (own_diag) {
+                const double2 zk = *reinterpret_cast<const double2*>(zp);
+                za = fma(Y.a, zk.x, za); zb = fma(Y.b, zk.y, zb);
+              }
+              if (k + 1 >= k1) break;
+              pY += pitch; pX += pitch; pitch -= 64;
+              if (k + 2 < k1) {
+                Y = tile_load(pY, 0);
+#pragma unroll
+                for (int t = T0; t < T; ++t) X[t] = tile_load(pX + t * NW * 64, 0);
+              }
+#pragma unroll
+              for (int t = T0; t < T; ++t) dmma884(S1[t].a, S1[t].b, Xn[t].a, Yn.a);
+#pragma unroll
+              for (int t = T0; t < T; ++t) dmma884(S1[t].a, S1[t].b, Xn[t].b, Yn.b);
+              if (own_diag) {
+                const double2 zk = *reinterpret_cast<const double2*>(zp + 8);
+                za = fma(Yn.a, zk.x, za); zb = fma(Yn.b, zk.y, zb);
+              }
+              zp += 16;
+            }
+          };
+          auto both = [&](auto t0c) {
+            pass(t0c, 0, j < h ? j : h, poolL + c * 64);          // columns k < min(j, h)
+            if (j > h) pass(t0c, h, j, poolL + (c - h) * 64);     // columns h <= k < j
+          };
+          if (T == 1 || t0 == 0) both(FitIC<0>{});
+          else if (T == 2 || t0 == 1) both(FitIC<(T > 1 ? 1 : 0)>{});
+          else if (T == 3 || t0 == 2) both(FitIC<(T > 2 ? 2 : 0)>{});
+          else both(FitIC<(T > 3 ? 3 : 0)>{});
+          FIT_STAMP(0);
+          // Ky tiles of column c (never stored); the diagonal row's partial result goes to the diagonal warp
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const int i = w + NW * t;
+            if (t >= t0 && i < nt) {
+              S0[t].a += S1[t].a; S0[t].b += S1[t].b;
+              Kn[t] = ky_tile(i, c, dadd);
+              if (i == c) tile_store(dpart[c & 1], lane, tile2{Kn[t].a - S0[t].a, Kn[t].b - S0[t].b});
+            }
+          }
+        }
+        FIT_STAMP(1);
+        named_bar_sync(1, FIT_THREADS);                             // inv(L_jj) published
+        FIT_STAMP(2);
+        // ---- (d) rows below the diagonal: L(i,j) = C(i,j) inv(L_jj)^T -> registers, pool, global; z_j ----
+        {
+          const tile2 Yinv = tile_load(linv, lane);
+          double* colj = Lp + (long long)tile_index(j, j, nt) * 64;
+          double* pcol = pool + pool_idx(j, j) * 64;
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const int i = w + NW * t;
+            if (i > j && i < nt) {
+              tile2 L{0.0, 0.0};
+              tile_mma(L, Ccur[t], Yinv);
+              Lt[t] = L;
+              tile_store(pcol + (i - j) * 64, lane, L);
+              tile_store(colj + (i - j) * 64, lane, L);
+            }
+          }
+          if (w == j % NW) {
+            // z_j = inv(L_jj) (y_j - sum_k L(j,k) z_k): reduce the lane partials over q, then an 8x8 mat-vec in-warp
+            double s = za + zb;
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            const double tr = ys[8 * j + r] - s;                                   // t[r], same on the 4 lanes of row r
+            const double t0v = __shfl_sync(0xffffffffu, tr, 8 * q), t1v = __shfl_sync(0xffffffffu, tr, 8 * q + 4);
+            double zv = fma(Yinv.a, t0v, Yinv.b * t1v);
+            zv += __shfl_xor_sync(0xffffffffu, zv, 1);
+            zv += __shfl_xor_sync(0xffffffffu, zv, 2);
+            if (q == 0) zs[8 * j + r] = zv;
+            za = 0.0; zb = 0.0;
+          }
+        }
+        FIT_STAMP(3);
+        named_bar_sync(2, FIT_THREADS);
+        FIT_STAMP(4);
+        // ---- (a) finish column c with the k = j term (X operand: the factor tile this warp has just produced) ----
+        if (c < nt) {
+          const tile2 Y = tile_load(pool + pool_idx(c, j) * 64, lane);
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const int i = w + NW * t;
+            if (i > c && i < nt) {
+              tile_mma(S0[t], Lt[t], Y);
+              Ccur[t] = tile2{Kn[t].a - S0[t].a, Kn[t].b - S0[t].b};
+            }
+          }
+          if (own_diag) {
+            const double2 zk = *reinterpret_cast<const double2*>(zs + 8 * j + 2 * q);
+            za = fma(Y.a, zk.x, za); zb = fma(Y.b, zk.y, zb);
+          }
+        }
+        FIT_STAMP(5);
+      }
+    }
+#ifdef CNGP_FIT_TIMING
+    if (lane == 0 && blockIdx.x == 0)
+      for (int k = 0; k < 6; ++k) a.dbg[w * 8 + k] += t_acc[k];
+#endif
+    __syncthreads();
+    fail_pivot = s_fail;
+    attempts_used = attempt;
+    if (fail_pivot == 0) break;
+    __syncthreads();
+  }
+
+  // ---- outputs: z, quad = z'z, logdet = 2 sum log L_kk, lml ----
+  double* zp = a.z + lp * (long long)(nt * 8);
+  double qs = 0.0, hl = 0.0;
+  for (int i = tid; i < nt * 8; i += FIT_THREADS) {
+    const double v = zs[i];
+    zp[i] = v;
+    qs += v * v;
+    hl += log(dpiv[i]);      // padded rows have pivot 1
+  }
+  for (int o = 16; o; o >>= 1) {
+    qs += __shfl_xor_sync(0xffffffffu, qs, o);
+    hl += __shfl_xor_sync(0xffffffffu, hl, o);
+  }
+  if (lane == 0) { s_red[w] = qs; s_red2[w] = hl; }
+  __syncthreads();
+  if (tid == 0) {
+    double quad = 0.0, hls = 0.0;
+    for (int i = 0; i <= NW; ++i) { quad += s_red[i]; hls += s_red2[i]; }
+    const double logdet = 2.0 * hls;
+    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+    const bool bad = fail_pivot != 0;
+    if (a.quad) a.quad[p] = bad ? nanv : quad;
+    if (a.logdet) a.logdet[p] = bad ? nanv : logdet;
+    if (a.lml) a.lml[p] = bad ? nanv : 0.5 * (-(double)N * CNGP_LOG_2PI - logdet - quad);
+    if (a.status) a.status[p] = bad ? -fail_pivot : attempts_used;
+  }
+}
+
+}  // namespace cngp
