@@ -106,7 +106,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -345,7 +345,7 @@ def run_ours(args):
             except Exception:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": "failed: " + (r.stderr or r.stdout)[-200:]}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -353,7 +353,31 @@ def run_ours(args):
     return 0
 
 
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version banner on
+    stdout at communicator creation), so file descriptor 1 is pointed at stderr for the run and the result line is
+    written to the original stdout."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -368,10 +392,10 @@ def main():
         thr, _ = cpu_port_throughput(1, cores)
         per_core = int(max(1, min(64, round(12.0 * thr / cores))))
         v, dt = cpu_port_throughput(per_core, cores)
-        print(json.dumps({"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+        emit({"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                           "sample": f"{per_core * cores} windows of the same workload in {dt:.1f} s "
                                     f"(oracle/gp_oracle.py, vectorised {M_TEST}-RHS dtrtrs), {cores} processes x 1 BLAS "
-                                    f"thread"}))
+                                    f"thread"})
         return 0
     return run_ours(args)
 
