@@ -32,6 +32,11 @@ class StopConfig(C.Structure):
                 ("init_llh", C.c_double * 3), ("init_ecef", C.c_double * 3)]
 
 
+class SlipConfig(C.Structure):   # cngp_slip_config
+    _fields_ = [("wheel_radius", C.c_double), ("cmd_min", C.c_double), ("rear_min", C.c_double),
+                ("arm_delay", C.c_int32), ("window", C.c_int32), ("min_samples", C.c_int32), ("reserved", C.c_int32)]
+
+
 class LargePlan(C.Structure):
     _fields_ = [("N", c_i64), ("n_pad", c_i64), ("world", c_i32), ("rank", c_i32), ("row_tiles", c_i64),
                 ("n_blockcols", c_i64), ("n_local_blockcols", c_i64), ("local_doubles", c_i64),
@@ -68,6 +73,9 @@ SIGNATURES = {
     "cngp_zupt_lookahead_batch": (C.c_int, [c_vp, c_dp, c_dp, c_i64, c_i32, c_dp, c_dp, c_dp, c_dp, c_dp, c_i32,
                                             C.POINTER(StopConfig), c_ip, c_ip, c_ip, c_dp, c_i32]),
     "cngp_llh_to_enu": (C.c_int, [c_vp, c_dp, c_i64, C.POINTER(StopConfig), c_dp, c_i32]),
+    "cngp_default_slip_config": (None, [C.POINTER(SlipConfig)]),
+    "cngp_slip_record_batch": (C.c_int, [c_vp, c_dp, c_dp, c_dp, c_dp, c_dp, c_i64, c_i32, C.POINTER(SlipConfig), c_i32,
+                                         c_i32, c_dp, c_dp, c_dp, c_ip, c_ip, c_ip, c_ip, c_i32]),
     "cngp_chol_large": (C.c_int, [c_vp, C.POINTER(Kernel), c_dp, c_dp, c_dp, c_i64, c_dp, c_dp, c_dp, c_dp, c_i32]),
     "cngp_large_make_plan": (C.c_int, [c_i64, c_i32, c_i32, C.POINTER(LargePlan)]),
     "cngp_large_assemble": (C.c_int, [c_vp, C.POINTER(LargePlan), C.POINTER(Kernel), c_dp, c_dp, c_dp, c_dp]),

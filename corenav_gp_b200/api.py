@@ -267,6 +267,41 @@ class GpContext:
         self._check(rc, "cngp_zupt_lookahead_batch")
         return dict(triggered=trig, i_stop=i_stop, step_stop=step, xy_err=xy)
 
+    @staticmethod
+    def slip_config(**over) -> L.SlipConfig:
+        c = L.SlipConfig()
+        L.load().cngp_default_slip_config(C.byref(c))
+        for key, v in over.items():
+            setattr(c, key, v)
+        return c
+
+    def slip_record(self, joint, att, vel, cmd, stop_cmd=None, max_windows: int = 2, cap: int = 149,
+                    cfg: Optional[L.SlipConfig] = None, want_slip: bool = True):
+        """Slip extraction + GP_Input recorder of CoreNav::Update for B drives (CoreNav.cpp:244-329).
+
+        joint [B,T,4], att [B,T,3], vel [B,T,3], cmd [B,T], stop_cmd [B,T] (NaN = no command) or None.  Returns
+        dict(slip [B,T], time_array / slip_array [B,W,cap], n_samples / published / stop_update [B,W], n_windows [B])."""
+        dev = _is_cuda(joint)
+        B, T = tuple(cmd.shape)
+        cfg = cfg or self.slip_config()
+        slip = self._empty((B, T), np.float64, dev) if want_slip else None
+        ta = self._empty((B, max_windows, cap), np.float64, dev)
+        sa = self._empty((B, max_windows, cap), np.float64, dev)
+        ns = self._empty((B, max_windows), np.int32, dev)
+        pu = self._empty((B, max_windows), np.int32, dev)
+        su = self._empty((B, max_windows), np.int32, dev)
+        nw = self._empty((B,), np.int32, dev)
+        a = [_Arg(joint, np.float64, dev), _Arg(att, np.float64, dev), _Arg(vel, np.float64, dev),
+             _Arg(cmd, np.float64, dev), _Arg(stop_cmd, np.float64, dev, True), _Arg(slip, np.float64, dev, True),
+             _Arg(ta, np.float64, dev), _Arg(sa, np.float64, dev), _Arg(ns, np.int32, dev), _Arg(pu, np.int32, dev),
+             _Arg(su, np.int32, dev), _Arg(nw, np.int32, dev)]
+        self._bind_stream(dev)
+        rc = self.lib.cngp_slip_record_batch(self.h, a[0].ptr, a[1].ptr, a[2].ptr, a[3].ptr, a[4].ptr, B, T,
+                                             C.byref(cfg), max_windows, cap, a[5].ptr, a[6].ptr, a[7].ptr, a[8].ptr,
+                                             a[9].ptr, a[10].ptr, a[11].ptr, L.MEM_DEVICE if dev else L.MEM_HOST)
+        self._check(rc, "cngp_slip_record_batch")
+        return dict(slip=slip, time_array=ta, slip_array=sa, n_samples=ns, published=pu, stop_update=su, n_windows=nw)
+
     def llh_to_enu(self, llh, cfg: Optional[L.StopConfig] = None):
         dev = _is_cuda(llh)
         n = int(np.prod(tuple(llh.shape))) // 3

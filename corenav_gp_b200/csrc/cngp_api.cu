@@ -21,6 +21,9 @@ extern "C" int cngp_launch_lookahead(const double*, const double*, long long, in
                                      const double*, const double*, const double*, int, const cngp_stop_config*, int*,
                                      int*, int*, double*, cudaStream_t);
 extern "C" int cngp_launch_llh_to_enu(const double*, long long, const cngp_stop_config*, double*, cudaStream_t);
+extern "C" int cngp_launch_slip_record(const double*, const double*, const double*, const double*, const double*, long long,
+                                       int, const cngp_slip_config*, int, int, double*, double*, double*, int*, int*, int*,
+                                       int*, cudaStream_t);
 
 using namespace cngp;
 
@@ -680,5 +683,58 @@ extern "C" int cngp_llh_to_enu(cngp_ctx* ctx, const double* llh, int64_t n, cons
   if (e) return fail(ctx, CNGP_ERR_CUDA, "llh_to_enu launch: %s", cudaGetErrorString((cudaError_t)e));
   const int rc = st.finish();
   if (rc) return fail(ctx, rc, "llh_to_enu: copy-out failed");
+  return CNGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// slip extraction + window recorder (the producer of GP_Input)
+// ------------------------------------------------------------------------------------------------------------
+extern "C" void cngp_default_slip_config(cngp_slip_config* c) {
+  c->wheel_radius = 0.11; c->cmd_min = 0.2; c->rear_min = 0.001; c->arm_delay = 10; c->window = 150; c->min_samples = 15;
+  c->reserved = 0;
+}
+
+extern "C" int cngp_slip_record_batch(cngp_ctx* ctx, const double* joint, const double* att, const double* vel,
+                                      const double* cmd, const double* stop_cmd, int64_t B, int32_t T,
+                                      const cngp_slip_config* cfg, int32_t max_windows, int32_t cap, double* slip,
+                                      double* time_array, double* slip_array, int32_t* n_samples, int32_t* published,
+                                      int32_t* stop_update, int32_t* n_windows, int32_t mem) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!joint || !att || !vel || !cmd || !time_array || !slip_array || !n_samples || !published || !stop_update ||
+      !n_windows || B < 0 || T <= 0 || max_windows <= 0 || cap <= 0)
+    return fail(ctx, CNGP_ERR_INVALID, "slip_record: bad argument");
+  if (B == 0) return CNGP_OK;
+  cngp_slip_config c;
+  if (cfg) c = *cfg; else cngp_default_slip_config(&c);
+  if (c.window <= 0 || c.arm_delay < 0) return fail(ctx, CNGP_ERR_INVALID, "slip_record: bad recorder configuration");
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  Stage st{ctx, mem};
+  const size_t bt = (size_t)B * T, bw = (size_t)B * max_windows;
+  const double* d_joint = (const double*)st.in(joint, sizeof(double) * bt * 4);
+  const double* d_att = (const double*)st.in(att, sizeof(double) * bt * 3);
+  const double* d_vel = (const double*)st.in(vel, sizeof(double) * bt * 3);
+  const double* d_cmd = (const double*)st.in(cmd, sizeof(double) * bt);
+  const double* d_scmd = (const double*)st.in(stop_cmd, sizeof(double) * bt);
+  double* d_slip = (double*)st.out(slip, sizeof(double) * bt);
+  double* d_ta = (double*)st.out(time_array, sizeof(double) * bw * cap);
+  double* d_sa = (double*)st.out(slip_array, sizeof(double) * bw * cap);
+  int* d_ns = (int*)st.out(n_samples, sizeof(int) * bw);
+  int* d_pu = (int*)st.out(published, sizeof(int) * bw);
+  int* d_su = (int*)st.out(stop_update, sizeof(int) * bw);
+  int* d_nw = (int*)st.out(n_windows, sizeof(int) * (size_t)B);
+  if (st.err) return fail(ctx, st.err, "slip_record: staging failed");
+  // windows that never close and samples never recorded read as zero
+  cudaMemsetAsync(d_ta, 0, sizeof(double) * bw * cap, ctx->stream);
+  cudaMemsetAsync(d_sa, 0, sizeof(double) * bw * cap, ctx->stream);
+  cudaMemsetAsync(d_ns, 0, sizeof(int) * bw, ctx->stream);
+  cudaMemsetAsync(d_pu, 0, sizeof(int) * bw, ctx->stream);
+  cudaMemsetAsync(d_su, 0xff, sizeof(int) * bw, ctx->stream);
+  ctx->begin(CNGP_PROF_MISC);
+  const int e = cngp_launch_slip_record(d_joint, d_att, d_vel, d_cmd, d_scmd, B, T, &c, max_windows, cap, d_slip, d_ta,
+                                        d_sa, d_ns, d_pu, d_su, d_nw, ctx->stream);
+  ctx->end();
+  if (e) return fail(ctx, CNGP_ERR_CUDA, "slip_record launch: %s", cudaGetErrorString((cudaError_t)e));
+  const int rc = st.finish();
+  if (rc) return fail(ctx, rc, "slip_record: copy-out failed");
   return CNGP_OK;
 }

@@ -262,3 +262,34 @@ def window_sigmas(first: int, count: int, seed: int = SEED, lo: float = 0.2, hi:
     """Per-window initial horizontal sigma ~ U[lo, hi] m (configs[3]) so that some windows trigger and some never do."""
     ids = np.arange(first, first + count, dtype=np.int64)
     return lo + (hi - lo) * _uniforms(ids, seed, stream=7)
+
+
+def drives(first: int, count: int, T: int = 400, seed: int = SEED, stop_events: bool = True):
+    """Synthetic odometry logs for the slip recorder: dict(joint [B,T,4], att [B,T,3],
+    vel [B,T,3], cmd [B,T], stop_cmd [B,T]).  10 Hz updates: standstill for a per-drive lead-in, then a 0.8 m/s drive at
+    the survey heading with wheel slip of the slipVal.csv scale on the right/left wheel pairs, an occasional stuck phase
+    (slip clamps to 1) and, on some drives, a stop command shortly after the first window closes."""
+    ids = np.arange(first, first + count, dtype=np.int64)
+    k = np.arange(T)[None, :]
+    lead = (5 + 40 * _uniforms(ids, seed, stream=11)).astype(np.int64)[:, None]
+    driving = k >= lead
+    psi = INIT_ATT[2] + 0.05 * (_uniforms(ids, seed, stream=12)[:, None] - 0.5) + 0.002 * np.sin(k / 23.0)
+    the = 0.03 * np.sin(k / 31.0 + 6.0 * _uniforms(ids, seed, stream=13)[:, None])
+    phi = 0.01 * np.cos(k / 17.0) + 0.0 * psi
+    stuck = (_uniforms(ids, seed, stream=17)[:, None] < 0.3) & (k > lead + 60) & (k < lead + 70)
+    v = np.where(stuck, -0.05, np.where(driving, 0.8, 0.0))      # stuck: wheels spin, the rover creeps backwards
+    vel = np.stack([v * np.cos(psi) * np.cos(the), v * np.sin(psi) * np.cos(the), -v * np.sin(the)], axis=-1)
+    vel = vel + 0.002 * _normals(ids, 3 * T, seed, stream=14).reshape(count, T, 3)
+    slip_r = 0.02 + 0.05 * np.sin(2 * np.pi * k / 37.0) + 0.03 * _normals(ids, T, seed, stream=15)
+    slip_l = slip_r + 0.01 * _normals(ids, T, seed, stream=16)
+    wr = np.where(stuck, 1.0, v / (1.0 - slip_r))       # wheel speed (m/s): slip = (v_wheel - v) / v_wheel
+    wl = np.where(stuck, 1.0, v / (1.0 - slip_l))
+    R = 0.11
+    joint = np.stack([-wl / R, wr / R, -wl / R * 0.999, wr / R * 1.001], axis=-1)
+    cmd = np.where(driving, 1.0, 0.0)
+    stop_cmd = np.full((count, T), np.nan)
+    if stop_events:
+        has = _uniforms(ids, seed, stream=18) < 0.5
+        at = np.minimum(T - 1, lead[:, 0] + 10 + 150 + 3)
+        stop_cmd[np.where(has)[0], at[has]] = 2.3
+    return dict(joint=joint, att=np.stack([phi, the, psi], axis=-1), vel=vel, cmd=cmd, stop_cmd=stop_cmd)

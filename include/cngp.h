@@ -16,6 +16,7 @@
  *                               (rows a9-a12), with the SetStopping response (core_navigation/srv/SetStopping.srv:1-7,
  *                               CoreNav.cpp:652-676) passed as plain arrays
  *   cngp_llh_to_enu             replaces GpPredictor::llh_to_enu, gp_predictor.cpp:144-178
+ *   cngp_slip_record_batch      replaces the slip extraction + GP_Input recorder of CoreNav::Update, CoreNav.cpp:244-329
  *   cngp_chol_large*            the N = 32768 single-window factorisation of BASELINE.json configs[4] (same math as a3)
  *
  * Conventions: plain C, int status returns (0 = ok, negative = error; text via cngp_last_error), no exceptions
@@ -191,6 +192,34 @@ int cngp_zupt_lookahead_batch(cngp_ctx* ctx, const double* mean, const double* s
 
 /* GpPredictor::llh_to_enu for n points on the device (lat, lon, h -> E, N, U); llh, enu [n][3]. */
 int cngp_llh_to_enu(cngp_ctx* ctx, const double* llh, int64_t n, const cngp_stop_config* cfg, double* enu, int32_t mem);
+
+/* Slip extraction + GP window recorder for B independent drives of T odometry updates each - the producer of
+ * core_nav/GP_Input.  Replaces CoreNav::Update, core_navigation/src/CoreNav.cpp:176-183, :190,
+ * :244-258 (slip = max over the four wheels of (v_wheel - vlin) / v_wheel, dead-band, clamp) and :264-329 (recorder).
+ *   joint     [B][T][4]  wheel joint rates (rad/s: front-left, front-right, back-left, back-right; CoreNav.cpp:178-181)
+ *   att       [B][T][3]  roll, pitch, yaw before the update (Cn2bUnc, CoreNav.cpp:190)
+ *   vel       [B][T][3]  INS velocity (nav frame) after the update (CoreNav.cpp:232,244)
+ *   cmd       [B][T]     cmd[0] of the drive command (CoreNav.cpp:264)
+ *   stop_cmd  [B][T]     seconds-to-stop received since the previous update (CoreNav.cpp:755-758), NaN = none; may be NULL
+ *   slip      [B][T]     per-update slip (may be NULL)
+ *   time_array, slip_array [B][max_windows][cap]   recorded windows (counts are 1-based update numbers, CoreNav.cpp:286)
+ *   n_samples, published, stop_update [B][max_windows]   samples recorded (may exceed cap: only cap are stored),
+ *                        published = n_samples >= 15 (CoreNav.cpp:300), index of the update that closed the window
+ *   n_windows [B]        windows closed (may exceed max_windows: only max_windows are stored) */
+typedef struct cngp_slip_config {
+  double wheel_radius;   /* InsConst.h:17   0.11 m */
+  double cmd_min;        /* CoreNav.cpp:264 0.2 */
+  double rear_min;       /* CoreNav.cpp:247 0.001 */
+  int32_t arm_delay;     /* CoreNav.cpp:270 10 updates */
+  int32_t window;        /* CoreNav.cpp:271 150 updates */
+  int32_t min_samples;   /* CoreNav.cpp:300 15 */
+  int32_t reserved;
+} cngp_slip_config;
+void cngp_default_slip_config(cngp_slip_config* cfg);
+int cngp_slip_record_batch(cngp_ctx* ctx, const double* joint, const double* att, const double* vel, const double* cmd,
+                           const double* stop_cmd, int64_t B, int32_t T, const cngp_slip_config* cfg,
+                           int32_t max_windows, int32_t cap, double* slip, double* time_array, double* slip_array,
+                           int32_t* n_samples, int32_t* published, int32_t* stop_update, int32_t* n_windows, int32_t mem);
 
 /* ---- large single window (BASELINE.json configs[4]: N = 32768) ----
  * Blocked right-looking FP64 Cholesky of Ky = K(x,x) + (noise + 1e-8) I - the same inference as cngp_predict_batch

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Device-timed numbers for the BASELINE.json configs that bench.py does not carry on its line.
 
-    python tools/bench_configs.py [sweep|mc|single|all] [scale]
+    python tools/bench_configs.py [sweep|mc|single|recorder|all] [scale]
 
   sweep  - configs[2]: Kernel Selection sweep, C = 64 candidates (8 kernel families x 8 hyper-parameter draws) x
            B = 4096 windows, N = 256, LML + gradient (cngp_lml_grad_batch).
@@ -149,6 +149,30 @@ def single(ctx):
             "triggered": int(out["triggered"][0]), "i_stop": int(out["i_stop"][0])}
 
 
+def recorder(ctx, scale):
+    """Row N1: slip extraction + recorder, 65536 drives x 512 updates resident in HBM (104 algorithmic bytes/update)."""
+    B, T = max(256, int(65536 * scale)), 512
+    chunk = 4096
+    base = syn.drives(0, chunk, T=T)
+    reps = B // chunk
+    dev = {k: torch.from_numpy(np.tile(v, (reps,) + (1,) * (v.ndim - 1))).cuda() for k, v in base.items()}
+    B = reps * chunk
+    ctx.set_profiling(True)
+    ctx.profile_read(5, reset=True)
+    ms, out = timed(lambda: ctx.slip_record(dev["joint"], dev["att"], dev["vel"], dev["cmd"], dev["stop_cmd"],
+                                            max_windows=2, cap=149), reps=3)
+    kms, kn = ctx.profile_read(5)
+    ctx.set_profiling(False)
+    ms_call, ms = ms, kms / max(1, kn)
+    byts = B * T * 104.0 + B * 2 * 149 * 16.0
+    return {"config": "N1 slip extraction + GP_Input recorder", "drives": B, "updates_per_drive": T, "ms": ms,
+            "updates_per_s": B * T / (ms * 1e-3), "algorithmic_GBps": byts / (ms * 1e-3) * 1e-9,
+            "ms_whole_call": ms_call,
+            "note": "ms = slip_record_kernel alone (CUDA events around the launch); the call also clears the outputs "
+                    "(five memsets); HBM peak 6453 GB/s (MEASURED_PEAKS.json)",
+            "windows_closed": int(out["n_windows"].sum().item())}
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
@@ -165,6 +189,8 @@ def main():
         lines.append(single(ctx))
     if what in ("sweep", "all") and rank == 0:
         lines.append(sweep(ctx, scale))
+    if what in ("recorder", "all") and rank == 0:
+        lines.append(recorder(ctx, scale))
     if what in ("mc", "all"):
         r = mc(ctx, scale, rank, world)
         if rank == 0:
