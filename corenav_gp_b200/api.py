@@ -267,6 +267,24 @@ class GpContext:
         self._check(rc, "cngp_zupt_lookahead_batch")
         return dict(triggered=trig, i_stop=i_stop, step_stop=step, xy_err=xy)
 
+    def ekf_context(self, llh, vel, att, f_ib_b, dt: float = 0.02, dt_odo: float = 0.1, want_h: bool = True):
+        """STM, Q (and the packed odometry H) of the SetStopping service for B operating points
+        (CoreNav::insErrorStateModel_LNF / calc_Q, CoreNav.cpp:411-527).  Inputs [B,3]; returns (STM [B,225], Q [B,225],
+        Hvec [B,60] or None)."""
+        dev = _is_cuda(llh)
+        B = int(tuple(llh.shape)[0])
+        S = self._empty((B, 225), np.float64, dev)
+        Q = self._empty((B, 225), np.float64, dev)
+        H = self._empty((B, 60), np.float64, dev) if want_h else None
+        a = [_Arg(llh, np.float64, dev), _Arg(vel, np.float64, dev), _Arg(att, np.float64, dev),
+             _Arg(f_ib_b, np.float64, dev), _Arg(S, np.float64, dev), _Arg(Q, np.float64, dev),
+             _Arg(H, np.float64, dev, True)]
+        self._bind_stream(dev)
+        rc = self.lib.cngp_ekf_context_batch(self.h, a[0].ptr, a[1].ptr, a[2].ptr, a[3].ptr, B, float(dt), float(dt_odo),
+                                             a[4].ptr, a[5].ptr, a[6].ptr, L.MEM_DEVICE if dev else L.MEM_HOST)
+        self._check(rc, "cngp_ekf_context_batch")
+        return S, Q, H
+
     @staticmethod
     def slip_config(**over) -> L.SlipConfig:
         c = L.SlipConfig()

@@ -21,6 +21,8 @@ extern "C" int cngp_launch_lookahead(const double*, const double*, long long, in
                                      const double*, const double*, const double*, int, const cngp_stop_config*, int*,
                                      int*, int*, double*, cudaStream_t);
 extern "C" int cngp_launch_llh_to_enu(const double*, long long, const cngp_stop_config*, double*, cudaStream_t);
+extern "C" int cngp_launch_ekf_context(const double*, const double*, const double*, const double*, long long, double, double,
+                                       double*, double*, double*, cudaStream_t);
 extern "C" int cngp_launch_slip_record(const double*, const double*, const double*, const double*, const double*, long long,
                                        int, const cngp_slip_config*, int, int, double*, double*, double*, int*, int*, int*,
                                        int*, cudaStream_t);
@@ -736,5 +738,35 @@ extern "C" int cngp_slip_record_batch(cngp_ctx* ctx, const double* joint, const 
   if (e) return fail(ctx, CNGP_ERR_CUDA, "slip_record launch: %s", cudaGetErrorString((cudaError_t)e));
   const int rc = st.finish();
   if (rc) return fail(ctx, rc, "slip_record: copy-out failed");
+  return CNGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// EKF context generation (STM, Q, H of the SetStopping service)
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int cngp_ekf_context_batch(cngp_ctx* ctx, const double* llh, const double* vel, const double* att,
+                                      const double* f_ib_b, int64_t B, double dt, double dt_odo, double* STM, double* Q,
+                                      double* Hvec, int32_t mem) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!llh || !vel || !att || !f_ib_b || !STM || !Q || B < 0 || !(dt > 0.0) || !(dt_odo > 0.0))
+    return fail(ctx, CNGP_ERR_INVALID, "ekf_context: bad argument");
+  if (B == 0) return CNGP_OK;
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  Stage st{ctx, mem};
+  const size_t b3 = sizeof(double) * 3 * (size_t)B;
+  const double* d_llh = (const double*)st.in(llh, b3);
+  const double* d_vel = (const double*)st.in(vel, b3);
+  const double* d_att = (const double*)st.in(att, b3);
+  const double* d_fib = (const double*)st.in(f_ib_b, b3);
+  double* d_S = (double*)st.out(STM, sizeof(double) * 225 * (size_t)B);
+  double* d_Q = (double*)st.out(Q, sizeof(double) * 225 * (size_t)B);
+  double* d_H = (double*)st.out(Hvec, sizeof(double) * 60 * (size_t)B);
+  if (st.err) return fail(ctx, st.err, "ekf_context: staging failed");
+  ctx->begin(CNGP_PROF_MISC);
+  const int e = cngp_launch_ekf_context(d_llh, d_vel, d_att, d_fib, B, dt, dt_odo, d_S, d_Q, d_H, ctx->stream);
+  ctx->end();
+  if (e) return fail(ctx, CNGP_ERR_CUDA, "ekf_context launch: %s", cudaGetErrorString((cudaError_t)e));
+  const int rc = st.finish();
+  if (rc) return fail(ctx, rc, "ekf_context: copy-out failed");
   return CNGP_OK;
 }

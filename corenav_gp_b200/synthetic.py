@@ -293,3 +293,21 @@ def drives(first: int, count: int, T: int = 400, seed: int = SEED, stop_events: 
         at = np.minimum(T - 1, lead[:, 0] + 10 + 150 + 3)
         stop_cmd[np.where(has)[0], at[has]] = 2.3
     return dict(joint=joint, att=np.stack([phi, the, psi], axis=-1), vel=vel, cmd=cmd, stop_cmd=stop_cmd)
+
+
+def operating_points(first: int, count: int, seed: int = SEED):
+    """Operating points for the EKF context generator: dict(llh, vel, att, f_ib_b), each [B,3] -
+    positions scattered ~100 m around the survey origin, 0.8 m/s drives at scattered headings and small tilts, the
+    specific force of a rover at rest on that tilt plus accelerometer noise."""
+    ids = np.arange(first, first + count, dtype=np.int64)
+    u = lambda st: _uniforms(ids, seed, stream=st)
+    llh = INIT_LLH[None, :] + np.stack([(u(21) - 0.5) * 3e-5, (u(22) - 0.5) * 3e-5, (u(23) - 0.5) * 10.0], axis=-1)
+    att = np.stack([(u(24) - 0.5) * 0.1, (u(25) - 0.5) * 0.2, (u(26) - 0.5) * 2 * np.pi], axis=-1)
+    speed = 0.4 + 0.8 * u(27)
+    vel = np.stack([speed * np.cos(att[:, 2]) * np.cos(att[:, 1]), speed * np.sin(att[:, 2]) * np.cos(att[:, 1]),
+                    -speed * np.sin(att[:, 1])], axis=-1)
+    g = 9.80665
+    f = np.stack([g * np.sin(att[:, 1]), -g * np.sin(att[:, 0]) * np.cos(att[:, 1]),
+                  -g * np.cos(att[:, 0]) * np.cos(att[:, 1])], axis=-1)
+    f = f + 0.05 * _normals(ids, 3, seed, stream=28)
+    return dict(llh=llh, vel=vel, att=att, f_ib_b=f)

@@ -17,6 +17,7 @@
  *                               CoreNav.cpp:652-676) passed as plain arrays
  *   cngp_llh_to_enu             replaces GpPredictor::llh_to_enu, gp_predictor.cpp:144-178
  *   cngp_slip_record_batch      replaces the slip extraction + GP_Input recorder of CoreNav::Update, CoreNav.cpp:244-329
+ *   cngp_ekf_context_batch      replaces insErrorStateModel_LNF / calc_Q (CoreNav.cpp:411-527) behind SetStopping
  *   cngp_chol_large*            the N = 32768 single-window factorisation of BASELINE.json configs[4] (same math as a3)
  *
  * Conventions: plain C, int status returns (0 = ok, negative = error; text via cngp_last_error), no exceptions
@@ -192,6 +193,16 @@ int cngp_zupt_lookahead_batch(cngp_ctx* ctx, const double* mean, const double* s
 
 /* GpPredictor::llh_to_enu for n points on the device (lat, lon, h -> E, N, U); llh, enu [n][3]. */
 int cngp_llh_to_enu(cngp_ctx* ctx, const double* llh, int64_t n, const cngp_stop_config* cfg, double* enu, int32_t mem);
+
+/* EKF context generation for B operating points: the matrices CoreNav serves through
+ * SetStopping (row a9), computed on the device for Monte-Carlo look-ahead runs.  Replaces the pure functions
+ * CoreNav::insErrorStateModel_LNF (core_navigation/src/CoreNav.cpp:411-470) and CoreNav::calc_Q (:471-527) evaluated
+ * as CoreNav::Propagate does (:58-72), and the odometry H of :191-220 in its instantaneous form.
+ *   llh [B][3] lat, lon (rad), height (m); vel [B][3] nav-frame velocity; att [B][3] roll, pitch, yaw;
+ *   f_ib_b [B][3] specific force (body); dt IMU step (s); dt_odo odometry step (s, H24 divides by it)
+ *   STM, Q [B][225] row-major 15x15; Hvec [B][60] packed as HvecData[r*4+c] (CoreNav.cpp:669-673); Hvec may be NULL */
+int cngp_ekf_context_batch(cngp_ctx* ctx, const double* llh, const double* vel, const double* att, const double* f_ib_b,
+                           int64_t B, double dt, double dt_odo, double* STM, double* Q, double* Hvec, int32_t mem);
 
 /* Slip extraction + GP window recorder for B independent drives of T odometry updates each - the producer of
  * core_nav/GP_Input.  Replaces CoreNav::Update, core_navigation/src/CoreNav.cpp:176-183, :190,
