@@ -13,4 +13,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --cs
 bash tools/ncu_capture.sh var_$TAG gp_var python tools/prof_predict.py 4096 256 600 1 > /dev/null 2>&1
 bash tools/ncu_capture.sh fit_$TAG gp_fit python tools/prof_predict.py 4096 256 600 1 > /dev/null 2>&1
 timeout 600 python tools/bench_large.py 32768 3 > $O/bench_large_$TAG.json 2> $O/bench_large_$TAG.err
+timeout 600 python tools/bench_configs.py all > $O/bench_configs_$TAG.json 2> $O/bench_configs_$TAG.err
 tail -3 $O/pytest_gpu_$TAG.log; tail -2 $O/smoke_$TAG.log; cat $O/bench_$TAG.json | cut -c1-1500; tail -2 $O/bench_$TAG.err
