@@ -168,6 +168,14 @@ __global__ void __launch_bounds__(LA_WARPS * 32) zupt_lookahead_kernel(const Loo
   llh_to_enu_dev(lat, lon, hgt, lk, cfg, enu0);
   __syncwarp();
 
+  // unit rows 9..14 in the STM (true for every CoreNav::insErrorStateModel_LNF output): see the propagation below
+  bool unit_ok = true;
+  for (int i = lane; i < 90; i += 32) {
+    const int rr = 9 + i / 15, cc = i % 15;
+    unit_ok = unit_ok && F[rr * 15 + cc] == (rr == cc ? 1.0 : 0.0);
+  }
+  const bool bias_rows_identity = __all_sync(0xffffffffu, unit_ok);
+
   const double* mean = a.mean + b * a.M;
   const double* sigma = a.sigma + b * a.M;
   const int nsteps = cfg.ratio * a.M;
@@ -176,30 +184,74 @@ __global__ void __launch_bounds__(LA_WARPS * 32) zupt_lookahead_kernel(const Loo
 
   for (int slip_i = 0; slip_i < nsteps; ++slip_i) {
     // ---- P = F P F' + Q ----
+    if (bias_rows_identity) {
+      // Rows 9..14 of the STM are unit rows (the bias states are constants, CoreNav.cpp:462-468), so rows 9..14 of F P are
+      // rows of P and columns 9..14 of (F P) F' are columns of F P: 90 of the 225 entries of each product are copies.
+      // The copied value is what the full dot product returns (every other term is an exact zero), so the result is
+      // unchanged up to the sign of zeros.
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int idx = lane + 32 * t;
-      if (idx < 225) {
-        const int rr = idx / 15, kk = idx % 15;
-        double acc = 0.0;
+      for (int t = 0; t < 5; ++t) {
+        const int idx = lane + 32 * t;         // rows 0..8 are the first 135 entries
+        if (idx < 135) {
+          const int rr = idx / 15, kk = idx % 15;
+          double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < 15; ++j) acc = fma(F[rr * 15 + j], P[j * 15 + kk], acc);
-        T[idx] = acc;
+          for (int j = 0; j < 15; ++j) acc = fma(F[rr * 15 + j], P[j * 15 + kk], acc);
+          T[idx] = acc;
+        }
       }
-    }
-    __syncwarp();
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int idx = lane + 32 * t;
-      if (idx < 225) {
-        const int rr = idx / 15, cc = idx % 15;
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < 15; ++k) acc = fma(T[rr * 15 + k], F[cc * 15 + k], acc);
-        P[idx] = acc + Q[idx];
+      for (int t = 0; t < 3; ++t) {
+        const int idx = 135 + lane + 32 * t;
+        if (idx < 225) T[idx] = P[idx];
       }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 5; ++t) {
+        const int e = lane + 32 * t;
+        if (e < 135) {
+          const int rr = e / 9, cc = e % 9, idx = rr * 15 + cc;
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < 15; ++k) acc = fma(T[rr * 15 + k], F[cc * 15 + k], acc);
+          P[idx] = acc + Q[idx];
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int e = lane + 32 * t;
+        if (e < 90) {
+          const int idx = (e / 6) * 15 + 9 + e % 6;
+          P[idx] = T[idx] + Q[idx];
+        }
+      }
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int idx = lane + 32 * t;
+        if (idx < 225) {
+          const int rr = idx / 15, kk = idx % 15;
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j < 15; ++j) acc = fma(F[rr * 15 + j], P[j * 15 + kk], acc);
+          T[idx] = acc;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int idx = lane + 32 * t;
+        if (idx < 225) {
+          const int rr = idx / 15, cc = idx % 15;
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < 15; ++k) acc = fma(T[rr * 15 + k], F[cc * 15 + k], acc);
+          P[idx] = acc + Q[idx];
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
     if (slip_i % cfg.ratio == 0) {
       // ---- UT -> R_IP, K = P H' (H P H' + R)^-1, Joseph update ----
       double Rl[16];
