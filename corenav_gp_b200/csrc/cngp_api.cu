@@ -43,6 +43,7 @@ struct cngp_ctx {
   cngp_config cfg;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // host-memory calls: results of one slab go home while the next slab computes
   std::string err;
   long long launches = 0;
   double* scratch = nullptr;  // factors (L / W tiles) + z
@@ -311,6 +312,7 @@ extern "C" void cngp_destroy(cngp_ctx* ctx) {
     if (b.p) cudaFree(b.p);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
 
@@ -383,10 +385,20 @@ struct Stage {
     outs.push_back({host, d, bytes});
     return d;
   }
+  const void* in_alloc(const void* host, size_t bytes) {   // device room only: the caller issues the copies
+    if (!host || bytes == 0 || mem == CNGP_MEM_DEVICE) return host;
+    void* d = ctx->buf(slot++, bytes);
+    if (!d) err = CNGP_ERR_NOMEM;
+    return d;
+  }
+  void forget(void* host) {   // this output is copied home by the caller
+    for (auto& o : outs)
+      if (o.host == host) o.bytes = 0;
+  }
   int finish() {
     if (mem == CNGP_MEM_DEVICE) return err;
     for (auto& o : outs)
-      if (cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) err = CNGP_ERR_CUDA;
+      if (o.bytes && cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) err = CNGP_ERR_CUDA;
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) err = CNGP_ERR_CUDA;
     return err;
   }
@@ -459,9 +471,12 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
   if ((rc = ensure_scratch(ctx))) return rc;
 
   Stage st{ctx, mem};
+  // Host-memory calls work in slabs: x / y of slab k+1 arrive and mean / var of slab k-1 leave on a second stream while
+  // slab k computes (16 x (N + M) bytes per window cross PCIe).
+  const bool pipelined = mem == CNGP_MEM_HOST && M > 0 && B >= 1024;
   const double* d_theta = (const double*)st.in(theta, sizeof(double) * (theta_stride ? (size_t)B * theta_stride : P));
-  const double* d_x = (const double*)st.in(x, sizeof(double) * (size_t)B * N);
-  const double* d_y = (const double*)st.in(y, sizeof(double) * (size_t)B * N);
+  const double* d_x = (const double*)(pipelined ? st.in_alloc(x, sizeof(double) * (size_t)B * N) : st.in(x, sizeof(double) * (size_t)B * N));
+  const double* d_y = (const double*)(pipelined ? st.in_alloc(y, sizeof(double) * (size_t)B * N) : st.in(y, sizeof(double) * (size_t)B * N));
   const double* d_xs = M ? (const double*)st.in(xstar, sizeof(double) * (xstar_stride ? (size_t)B * xstar_stride : M)) : nullptr;
   double* d_mean = M ? (double*)st.out(mean, sizeof(double) * (size_t)B * M) : nullptr;
   double* d_var = M ? (double*)st.out(var, sizeof(double) * (size_t)B * M) : nullptr;
@@ -477,9 +492,32 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
   const int kid = match_fast_kernel(kp);
   const size_t per_problem = ((size_t)tiles_in_lower(nt) * 64 + (size_t)nt * 8 * 5) * sizeof(double);
   const size_t slack = 64 * 64;   // >= the largest chunk (tiles x 64 doubles)   // gp_var_kernel's first (partial) chunk may start before the first tile
-  const long long chunk = std::max<long long>(1, (long long)((ctx->scratch_bytes - slack * 8) / per_problem));
+  long long chunk = std::max<long long>(1, (long long)((ctx->scratch_bytes - slack * 8) / per_problem));
+  cudaEvent_t pending_inputs = nullptr;
+  auto send_inputs = [&](long long w0, cudaStream_t s) -> int {   // x, y of the slab starting at w0
+    if (w0 >= B) return 0;
+    const long long nw = std::min<long long>(chunk, B - w0);
+    const size_t off = (size_t)w0 * N, bytes = sizeof(double) * (size_t)nw * N;
+    if (cudaMemcpyAsync((double*)d_x + off, x + off, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return 1;
+    if (cudaMemcpyAsync((double*)d_y + off, y + off, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return 1;
+    return 0;
+  };
+  if (pipelined) {
+    if (!ctx->copy_stream && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+      return fail(ctx, CNGP_ERR_CUDA, "predict: cudaStreamCreate failed");
+    chunk = std::min<long long>(chunk, (B + 3) / 4);
+    st.forget(mean);
+    st.forget(var);
+    if (send_inputs(0, ctx->stream)) return fail(ctx, CNGP_ERR_CUDA, "predict: input copy failed");
+  }
   for (long long w0 = 0; w0 < B; w0 += chunk) {
     const long long nw = std::min<long long>(chunk, B - w0);
+    if (pipelined && w0 + chunk < B) {   // next slab's inputs travel while this slab computes
+      if (send_inputs(w0 + chunk, ctx->copy_stream)) return fail(ctx, CNGP_ERR_CUDA, "predict: input copy failed");
+      cudaEvent_t arrived = ctx->get_event();
+      CU(ctx, cudaEventRecord(arrived, ctx->copy_stream));
+      pending_inputs = arrived;
+    }
     double* Lbuf = ctx->scratch + slack;
     double* zbuf = Lbuf + (size_t)nw * tiles_in_lower(nt) * 64;
     double* fbuf = zbuf + (size_t)nw * nt * 8;
@@ -518,8 +556,23 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
       if (vrc) return fail(ctx, vrc, "predict: staging buffer for the generic kernel path");
     }
     CU(ctx, cudaGetLastError());
+    if (pipelined) {
+      cudaEvent_t done = ctx->get_event();
+      CU(ctx, cudaEventRecord(done, ctx->stream));
+      CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, done, 0));
+      const size_t off = (size_t)w0 * M, bytes = sizeof(double) * (size_t)nw * M;
+      CU(ctx, cudaMemcpyAsync(mean + off, d_mean + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      CU(ctx, cudaMemcpyAsync(var + off, d_var + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      ctx->event_pool.push_back(done);   // its wait is enqueued: free for re-use
+      if (pending_inputs) {               // the next slab may start once its inputs have landed
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, pending_inputs, 0));
+        ctx->event_pool.push_back(pending_inputs);
+        pending_inputs = nullptr;
+      }
+    }
   }
   rc = st.finish();
+  if (pipelined && cudaStreamSynchronize(ctx->copy_stream) != cudaSuccess) rc = rc ? rc : CNGP_ERR_CUDA;
   if (rc) return fail(ctx, rc, "predict: copy-out failed: %s", cudaGetErrorString(cudaGetLastError()));
   return CNGP_OK;
 }

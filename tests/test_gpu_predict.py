@@ -136,3 +136,28 @@ def test_device_pointer_path_matches_host_path(gp_ctx):
     torch.cuda.synchronize()
     assert np.array_equal(m0, m1.cpu().numpy()) and np.array_equal(v0, v1.cpu().numpy())
     assert np.array_equal(l0, l1.cpu().numpy())
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_pipelined_host_path_matches_device_path(gp_ctx, pinned):
+    """Host-memory calls with B >= 1024 run in four slabs with the copies on a second stream (cngp_api.cu): ragged slab
+    sizes, per-window theta and xstar, pageable and pinned buffers - results equal the device-pointer path bit for bit."""
+    import torch
+    B, N, M = 1027, 40, 37
+    x, y = syn.slip_windows(7, B, N)
+    xs = np.stack([syn.test_grid(x[b], M) + 0.25 * (b % 3) for b in range(B)])
+    th = np.tile(syn.theta_for("rbf"), (B, 1)) * (1.0 + 0.1 * (np.arange(B) % 5))[:, None]
+    if pinned:
+        hx, hy, hxs, hth = (torch.from_numpy(a).pin_memory() for a in (x, y, xs, th))
+        out = (torch.empty(B, M, dtype=torch.float64).pin_memory(), torch.empty(B, M, dtype=torch.float64).pin_memory(),
+               torch.empty(B, dtype=torch.float64).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory())
+        m0, v0, l0, s0 = gp_ctx.predict("rbf", hth, hx, hy, hxs, out=out)
+        m0, v0, l0 = m0.numpy(), v0.numpy(), l0.numpy()
+    else:
+        m0, v0, l0, s0 = gp_ctx.predict("rbf", th, x, y, xs)
+    dx, dy, dxs, dth = (torch.from_numpy(a).cuda() for a in (x, y, xs, th))
+    m1, v1, l1, s1 = gp_ctx.predict("rbf", dth, dx, dy, dxs)
+    torch.cuda.synchronize()
+    assert np.array_equal(m0, m1.cpu().numpy()) and np.array_equal(v0, v1.cpu().numpy())
+    assert np.array_equal(l0, l1.cpu().numpy())
+    assert np.isfinite(m0).all() and (v0 > 0).all()
