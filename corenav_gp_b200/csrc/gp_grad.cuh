@@ -19,6 +19,7 @@ namespace cngp {
 
 constexpr int GRAD_WARPS = 8;
 constexpr int GRAD_THREADS = GRAD_WARPS * 32;
+constexpr int GRAD_FAST_LEAVES = 4;   // leaves with register accumulators of their own (larger expressions: generic scan)
 
 struct GradArgs {
   KProg kp;
@@ -48,6 +49,8 @@ __global__ void __launch_bounds__(GRAD_THREADS) gp_grad_kernel(const GradArgs a)
   __shared__ double zs[CNGP_MAX_N + 8];
   __shared__ double thv[CNGP_MAX_PARAMS + 1];
   __shared__ double gred[GRAD_WARPS][CNGP_MAX_PARAMS + 1];
+  __shared__ int leaf_t0[CNGP_MAX_LEAVES], leaf_t1[CNGP_MAX_LEAVES];   // bounds of the product term a leaf belongs to
+  __shared__ GradConst gcs[CNGP_MAX_LEAVES];
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int r = lane >> 2, q = lane & 3;
@@ -66,6 +69,9 @@ __global__ void __launch_bounds__(GRAD_THREADS) gp_grad_kernel(const GradArgs a)
     zs[i] = zp[i];
   }
   if (tid < P) thv[tid] = th[tid];
+  if (tid < a.kp.n_leaves) gcs[tid] = grad_prepare(a.kp.leaf_type[tid], th + a.kp.leaf_param[tid]);
+  if (tid < a.kp.n_terms)
+    for (int u = a.kp.term_start[tid]; u < a.kp.term_start[tid + 1]; ++u) { leaf_t0[u] = a.kp.term_start[tid]; leaf_t1[u] = a.kp.term_start[tid + 1]; }
   if (a.status[p] < 0) {  // factorisation failed: NaN gradient
     if (tid < P) a.grad[p * P + tid] = __longlong_as_double(0x7ff8000000000000LL);
     return;
@@ -115,6 +121,10 @@ __global__ void __launch_bounds__(GRAD_THREADS) gp_grad_kernel(const GradArgs a)
   double g[CNGP_MAX_PARAMS + 1];
 #pragma unroll
   for (int i = 0; i <= CNGP_MAX_PARAMS; ++i) g[i] = 0.0;
+  double gl[GRAD_FAST_LEAVES][3];
+#pragma unroll
+  for (int i = 0; i < GRAD_FAST_LEAVES; ++i) gl[i][0] = gl[i][1] = gl[i][2] = 0.0;
+  const bool few_leaves = a.kp.n_leaves <= GRAD_FAST_LEAVES;
   const int n_tiles = tiles_in_lower(nt);
   for (int t = w; t < n_tiles; t += GRAD_WARPS) {
     // t -> (ta >= tb) by rows of the lower triangle
@@ -146,23 +156,54 @@ __global__ void __launch_bounds__(GRAD_THREADS) gp_grad_kernel(const GradArgs a)
         double r2 = r2_expanded(xa, xb);
         if (same) r2 = 0.0;
         if (same) g[CNGP_MAX_PARAMS] += wgt;  // noise: trace(dL_dK)
-        for (int tt = 0; tt < a.kp.n_terms; ++tt) {
-          const int u0 = a.kp.term_start[tt], u1 = a.kp.term_start[tt + 1];
-          for (int u = u0; u < u1; ++u) {
-            double others = 1.0, dv[3];
-            for (int u2 = u0; u2 < u1; ++u2)
-              if (u2 != u)
-                others *= leaf_value_grad<true>(a.kp.leaf_type[u2], thv + a.kp.leaf_param[u2], xa, xb, r2, same, dv);
-            leaf_value_grad<true>(a.kp.leaf_type[u], thv + a.kp.leaf_param[u], xa, xb, r2, same, dv);
-            const int np = leaf_nparams(a.kp.leaf_type[u]);
-            const int po = a.kp.leaf_param[u];
-            const double ww = wgt * others;
+        if (few_leaves) {
+          // Expressions of up to GRAD_FAST_LEAVES leaves (every family of the Kernel Selection study): one accumulator
+          // triple per leaf under a compile-time index - no scan over the CNGP_MAX_PARAMS parameter slots per entry.
 #pragma unroll
-            for (int i = 0; i < CNGP_MAX_PARAMS; ++i) {
-              const int jj = i - po;
-              if (jj >= 0 && jj < np) g[i] += ww * (jj == 0 ? dv[0] : (jj == 1 ? dv[1] : dv[2]));
+          for (int ul = 0; ul < GRAD_FAST_LEAVES; ++ul) {
+            if (ul < a.kp.n_leaves) {
+              const int u0 = leaf_t0[ul], u1 = leaf_t1[ul];
+              double others = 1.0, dv[3];
+              for (int u2 = u0; u2 < u1; ++u2)
+                if (u2 != ul)
+                  others *= leaf_value_grad_c<true>(a.kp.leaf_type[u2], thv + a.kp.leaf_param[u2], gcs[u2], xa, xb, r2, same, dv);
+              leaf_value_grad_c<true>(a.kp.leaf_type[ul], thv + a.kp.leaf_param[ul], gcs[ul], xa, xb, r2, same, dv);
+              const double ww = wgt * others;
+              gl[ul][0] += ww * dv[0]; gl[ul][1] += ww * dv[1]; gl[ul][2] += ww * dv[2];
             }
           }
+        } else {
+          for (int tt = 0; tt < a.kp.n_terms; ++tt) {
+            const int u0 = a.kp.term_start[tt], u1 = a.kp.term_start[tt + 1];
+            for (int u = u0; u < u1; ++u) {
+              double others = 1.0, dv[3];
+              for (int u2 = u0; u2 < u1; ++u2)
+                if (u2 != u)
+                  others *= leaf_value_grad<true>(a.kp.leaf_type[u2], thv + a.kp.leaf_param[u2], xa, xb, r2, same, dv);
+              leaf_value_grad<true>(a.kp.leaf_type[u], thv + a.kp.leaf_param[u], xa, xb, r2, same, dv);
+              const int np = leaf_nparams(a.kp.leaf_type[u]);
+              const int po = a.kp.leaf_param[u];
+              const double ww = wgt * others;
+#pragma unroll
+              for (int i = 0; i < CNGP_MAX_PARAMS; ++i) {
+                const int jj = i - po;
+                if (jj >= 0 && jj < np) g[i] += ww * (jj == 0 ? dv[0] : (jj == 1 ? dv[1] : dv[2]));
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (few_leaves) {   // hand the per-leaf sums to their parameter slots
+#pragma unroll
+    for (int ul = 0; ul < GRAD_FAST_LEAVES; ++ul) {
+      if (ul < a.kp.n_leaves) {
+        const int np = leaf_nparams(a.kp.leaf_type[ul]), po = a.kp.leaf_param[ul];
+#pragma unroll
+        for (int i = 0; i < CNGP_MAX_PARAMS; ++i) {
+          const int jj = i - po;
+          if (jj >= 0 && jj < np) g[i] += (jj == 0 ? gl[ul][0] : (jj == 1 ? gl[ul][1] : gl[ul][2]));
         }
       }
     }

@@ -20,6 +20,8 @@ struct LeafConst {
   double c0, c1, c2;
 };
 
+__device__ __forceinline__ double fast_exp(double x);   // branch-free 16-operation exp for x <= ~1, defined below
+
 // Derived per-window constants of one leaf from its hyper-parameters.
 __device__ __forceinline__ LeafConst leaf_prepare(int type, const double* th) {
   LeafConst c{th[0], 0.0, 0.0};
@@ -44,19 +46,19 @@ __device__ __forceinline__ double r2_expanded(double xa, double xb) {
 template <bool SYM>
 __device__ __forceinline__ double leaf_value(int type, const LeafConst& c, double xa, double xb, double r2, bool same) {
   switch (type) {
-    case CNGP_K_RBF: return c.c0 * exp(r2 * c.c1);
+    case CNGP_K_RBF: return c.c0 * fast_exp(r2 * c.c1);
     case CNGP_K_MAT32: {
       const double r = sqrt(r2) * c.c1;
-      return c.c0 * (1.0 + r) * exp(-r);
+      return c.c0 * (1.0 + r) * fast_exp(-r);
     }
     case CNGP_K_MAT52: {
       const double r = sqrt(r2) * c.c1;
-      return c.c0 * (1.0 + r + r * r * (1.0 / 3.0)) * exp(-r);
+      return c.c0 * (1.0 + r + r * r * (1.0 / 3.0)) * fast_exp(-r);
     }
-    case CNGP_K_RATQUAD: return c.c0 * exp(-c.c2 * log1p(r2 * c.c1));
+    case CNGP_K_RATQUAD: return c.c0 * fast_exp(-c.c2 * log1p(r2 * c.c1));
     case CNGP_K_STDPERIODIC: {
       const double s = sin((xa - xb) * c.c1);
-      return c.c0 * exp(s * s * c.c2);
+      return c.c0 * fast_exp(s * s * c.c2);
     }
     case CNGP_K_BROWNIAN: {
       const bool agree = (xa > 0.0 && xb > 0.0) || (xa < 0.0 && xb < 0.0) || (xa == 0.0 && xb == 0.0);
@@ -150,6 +152,77 @@ __device__ __forceinline__ double leaf_value_grad(int type, const double* th, do
       dv[0] = e;
       dv[1] = th[0] * e * il2 * s * co * (base / th[1]);
       dv[2] = th[0] * e * s * s * il2 / th[2];
+      return th[0] * e;
+    }
+    case CNGP_K_BROWNIAN: {
+      const bool agree = (xa > 0.0 && xb > 0.0) || (xa < 0.0 && xb < 0.0) || (xa == 0.0 && xb == 0.0);
+      dv[0] = agree ? fmin(fabs(xa), fabs(xb)) : 0.0;
+      return th[0] * dv[0];
+    }
+    case CNGP_K_LINEAR: dv[0] = xa * xb; return th[0] * dv[0];
+    case CNGP_K_BIAS: dv[0] = 1.0; return th[0];
+    case CNGP_K_WHITE: dv[0] = (SYM && same) ? 1.0 : 0.0; return th[0] * dv[0];
+  }
+  return 0.0;
+}
+
+// The same with the reciprocals of the length scales taken once per problem (GradConst) instead of once per entry,
+// and the branch-free 16-operation exp: gp_grad_kernel evaluates N(N+1)/2 entries per problem.
+struct GradConst {
+  double i1, i1sq, i2;   // 1/th[1], 1/th[1]^2, 1/th[2] (or 1/th[2]^2 for the periodic leaf's i1sq)
+};
+__device__ __forceinline__ GradConst grad_prepare(int type, const double* th) {
+  GradConst c{0.0, 0.0, 0.0};
+  switch (type) {
+    case CNGP_K_RBF: case CNGP_K_MAT32: case CNGP_K_MAT52: case CNGP_K_RATQUAD:
+      c.i1 = 1.0 / th[1]; c.i1sq = 1.0 / (th[1] * th[1]); break;
+    case CNGP_K_STDPERIODIC: c.i1 = 1.0 / th[1]; c.i1sq = 1.0 / (th[2] * th[2]); c.i2 = 1.0 / th[2]; break;
+    default: break;
+  }
+  return c;
+}
+template <bool SYM>
+__device__ __forceinline__ double leaf_value_grad_c(int type, const double* th, const GradConst& c, double xa, double xb,
+                                                    double r2, bool same, double dv[3]) {
+  dv[0] = dv[1] = dv[2] = 0.0;
+  switch (type) {
+    case CNGP_K_RBF: {
+      const double e = fast_exp(-0.5 * r2 * c.i1sq);
+      dv[0] = e;
+      dv[1] = th[0] * e * r2 * c.i1sq * c.i1;
+      return th[0] * e;
+    }
+    case CNGP_K_MAT32: {
+      const double r = sqrt(r2) * (1.7320508075688772 * c.i1);
+      const double e = fast_exp(-r);
+      dv[0] = (1.0 + r) * e;
+      dv[1] = th[0] * r * r * e * c.i1;
+      return th[0] * dv[0];
+    }
+    case CNGP_K_MAT52: {
+      const double r = sqrt(r2) * (2.2360679774997897 * c.i1);
+      const double e = fast_exp(-r);
+      dv[0] = (1.0 + r + r * r * (1.0 / 3.0)) * e;
+      dv[1] = th[0] * (r * r * (1.0 + r) * (1.0 / 3.0)) * e * c.i1;
+      return th[0] * dv[0];
+    }
+    case CNGP_K_RATQUAD: {
+      const double h = 0.5 * r2 * c.i1sq;
+      const double l1p = log1p(h);
+      const double kr = fast_exp(-th[2] * l1p);
+      dv[0] = kr;
+      dv[1] = th[0] * kr * th[2] * (2.0 * h) * c.i1 / (1.0 + h);
+      dv[2] = -th[0] * kr * l1p;
+      return th[0] * kr;
+    }
+    case CNGP_K_STDPERIODIC: {
+      const double base = 3.14159265358979323846 * (xa - xb) * c.i1;
+      double s, co;
+      sincos(base, &s, &co);
+      const double e = fast_exp(-0.5 * s * s * c.i1sq);
+      dv[0] = e;
+      dv[1] = th[0] * e * c.i1sq * s * co * (base * c.i1);
+      dv[2] = th[0] * e * s * s * c.i1sq * c.i2;
       return th[0] * e;
     }
     case CNGP_K_BROWNIAN: {
