@@ -11,6 +11,7 @@
 // order as the C oracle, so (triggered, i) is reproducible bit for bit.  This translation unit is compiled with
 // -fmad=false: every fused operation below is an explicit fma().
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include "../../include/cngp.h"
 
 namespace cngp {
@@ -138,6 +139,31 @@ __device__ __forceinline__ void ut_R(double mean, double sigma, const cngp_stop_
     }
 }
 
+// Cheap rigorous upper bound of the horizontal ENU displacement between (lat, lon, h) and (lat + dl, lon + dm, h + dh):
+// walk the three coordinates one at a time.  The meridian and parallel chords are at most Rb dl and Rb cmax dm long
+// (Rb >= any radius of curvature + height, cmax >= |cos| along the way) and perpendicular up to dm / 2, the height step
+// only shows in the horizontal plane of init_llh through the tilt (<= tilt0 + dl + dm) between the two verticals.
+// While the bound stays below the threshold the exact observer (five trigonometric calls) cannot trigger and is skipped.
+struct ObsBound {
+  double habs, coslat0, tilt0;
+  bool usable;
+};
+__device__ __forceinline__ ObsBound obs_prepare(double lat, double lon, double h, const cngp_stop_config& c) {
+  ObsBound o;
+  o.habs = fabs(h);
+  o.coslat0 = fabs(cos(lat));
+  o.tilt0 = fabs(lat - c.init_llh[0]) + fabs(lon - c.init_llh[1]);
+  o.usable = fabs(lat) < 1.4;       // the closed form of gp_predictor.cpp:150-160 is the ellipsoid map away from the poles
+  return o;
+}
+__device__ __forceinline__ bool obs_cannot_trigger(const ObsBound& o, double dl, double dm, double dh, double thresh) {
+  const double Rb = 6.4e6 + o.habs + dh;
+  const double A = Rb * dl, Bq = Rb * (o.coslat0 + dl) * dm;
+  const double tilt = fmin(1.0, o.tilt0 + dl + dm);
+  const double bound = sqrt(A * A + Bq * Bq) * (1.0 + dm) + dh * tilt;
+  return o.usable && dl < 0.1 && (bound * (1.0 + 1e-9) + 1e-6 < thresh);     // NaN compares false: exact path
+}
+
 // per-warp shared-memory working set (doubles)
 constexpr int LA_P = 0, LA_T = 225, LA_A = 450, LA_PHT = 675, LA_K = 735, LA_KR = 795, LA_S = 855, LA_SI = 871,
               LA_R = 887, LA_F = 903, LA_Q = 1128, LA_H = 1353, LA_WS = 1413 + 3;  // padded to an even count
@@ -166,6 +192,7 @@ __global__ void __launch_bounds__(LA_WARPS * 32) zupt_lookahead_kernel(const Loo
   const LlhConst lk = llh_prepare(cfg);
   double enu0[3];
   llh_to_enu_dev(lat, lon, hgt, lk, cfg, enu0);
+  const ObsBound ob = obs_prepare(lat, lon, hgt, cfg);
   __syncwarp();
 
   // unit rows 9..14 in the STM (true for every CoreNav::insErrorStateModel_LNF output): see the propagation below
@@ -337,9 +364,12 @@ __global__ void __launch_bounds__(LA_WARPS * 32) zupt_lookahead_kernel(const Loo
       ++i_upd;
     }
     // ---- error observer: the five trigonometric values are spread over lanes 0..4 ----
-    const double lat3 = lat + 3.0 * sqrt(fabs(P[6 * 15 + 6]));
-    const double lon3 = lon + 3.0 * sqrt(fabs(P[7 * 15 + 7]));
-    const double h3 = hgt + 3.0 * sqrt(fabs(P[8 * 15 + 8]));
+    const double dl3 = 3.0 * sqrt(fabs(P[6 * 15 + 6])), dm3 = 3.0 * sqrt(fabs(P[7 * 15 + 7])),
+                 dh3 = 3.0 * sqrt(fabs(P[8 * 15 + 8]));
+    if (slip_i + 1 < nsteps && obs_cannot_trigger(ob, dl3, dm3, dh3, cfg.thresh)) continue;
+    const double lat3 = lat + dl3;
+    const double lon3 = lon + dm3;
+    const double h3 = hgt + dh3;
     double tv = 0.0;
     if (lane == 0) tv = sin(lat3);
     else if (lane == 1) tv = cos(lat3);
@@ -356,6 +386,176 @@ __global__ void __launch_bounds__(LA_WARPS * 32) zupt_lookahead_kernel(const Loo
     if (xy > cfg.thresh) { trig = 1; step = slip_i; break; }
   }
   if (lane == 0) {
+    a.triggered[b] = trig;
+    a.i_stop[b] = i_upd;
+    a.step_stop[b] = step;
+    a.xy_err[b] = xy;
+  }
+}
+
+// Small batches (the reference's own use: ONE window per callback, gp_predictor.cpp:16): the look-ahead is a chain of up
+// to 2995 dependent 15x15 steps, and one warp per window spends ~7 k cycles on each.  Here a CTA of 256 threads takes the
+// window - one thread per matrix entry, every dot product in the same ascending-index fma order as the warp kernel (so
+// the results are the same bits), the five trigonometric values of the observer on five different warps - which cuts
+// the step to about a seventh.  Used when the batch cannot fill the GPU with warps anyway (LA_CTA_MAX_B).
+constexpr int LA_CTA_THREADS = 256;
+constexpr long long LA_CTA_MAX_B = 592;   // 4 windows per SM
+
+__global__ void __launch_bounds__(LA_CTA_THREADS) zupt_lookahead_cta_kernel(const LookaheadArgs a) {
+  extern __shared__ double ws[];
+  __shared__ double trig5[5];
+  const int tid = threadIdx.x;
+  const long long b = blockIdx.x;
+  double *P = ws + LA_P, *T = ws + LA_T, *A = ws + LA_A, *PHt = ws + LA_PHT, *K = ws + LA_K, *KR = ws + LA_KR,
+         *S = ws + LA_S, *Si = ws + LA_SI, *R = ws + LA_R, *F = ws + LA_F, *Q = ws + LA_Q, *H = ws + LA_H;
+  const cngp_stop_config& cfg = a.cfg;
+  const int pw = a.per_window;
+  const double* gP = a.P + ((pw & CNGP_PERWIN_P) ? b * 225 : 0);
+  const double* gQ = a.Q + ((pw & CNGP_PERWIN_Q) ? b * 225 : 0);
+  const double* gF = a.STM + ((pw & CNGP_PERWIN_STM) ? b * 225 : 0);
+  const double* gH = a.Hvec + ((pw & CNGP_PERWIN_H) ? b * 60 : 0);
+  const double* gpos = a.pos + ((pw & CNGP_PERWIN_POS) ? b * 3 : 0);
+  if (tid < 225) { P[tid] = gP[tid]; Q[tid] = gQ[tid]; F[tid] = gF[tid]; }
+  if (tid < 60) {
+    const int rr = tid / 15, cc = tid % 15;
+    H[tid] = gH[cfg.fix_h_packing ? rr * 15 + cc : rr * 4 + cc];
+  }
+  const double lat = gpos[0], lon = gpos[1], hgt = gpos[2];
+  const LlhConst lk = llh_prepare(cfg);
+  double enu0[3];
+  llh_to_enu_dev(lat, lon, hgt, lk, cfg, enu0);
+  const ObsBound ob = obs_prepare(lat, lon, hgt, cfg);
+  __syncthreads();
+  bool unit_ok = true;
+  if (tid < 90) {
+    const int rr = 9 + tid / 15, cc = tid % 15;
+    unit_ok = F[rr * 15 + cc] == (rr == cc ? 1.0 : 0.0);
+  }
+  const bool bias_rows_identity = __syncthreads_and(unit_ok);
+
+  const double* mean = a.mean + b * a.M;
+  const double* sigma = a.sigma + b * a.M;
+  const int nsteps = cfg.ratio * a.M;
+  const bool ent = tid < 225;
+  const int rr = tid / 15, cc = tid % 15;      // entry (rr, cc) of a 15x15 matrix
+  const int r4 = tid / 4, m4 = tid % 4;        // entry (r4, m4) of a 15x4 matrix (tid < 60), (m4', n4) of 4x4 (tid < 16)
+  int i_upd = 0, trig = 0, step = nsteps;
+  double xy = 0.0;
+
+  for (int slip_i = 0; slip_i < nsteps; ++slip_i) {
+    // ---- P = F P F' + Q ----
+    if (ent) {
+      double acc;
+      if (bias_rows_identity && rr >= 9) {
+        acc = P[tid];
+      } else {
+        acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 15; ++j) acc = fma(F[rr * 15 + j], P[j * 15 + cc], acc);
+      }
+      T[tid] = acc;
+    }
+    __syncthreads();
+    if (ent) {
+      double acc;
+      if (bias_rows_identity && cc >= 9) {
+        acc = T[tid];
+      } else {
+        acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 15; ++k) acc = fma(T[rr * 15 + k], F[cc * 15 + k], acc);
+      }
+      P[tid] = acc + Q[tid];
+    }
+    __syncthreads();
+    if (slip_i % cfg.ratio == 0) {
+      // ---- UT -> R_IP, K = P H' (H P H' + R)^-1, Joseph update ----
+      double Rl[16];
+      ut_R(mean[i_upd], sigma[i_upd], cfg, Rl);
+      if (tid < 16) R[tid] = Rl[tid];
+      if (tid < 60) {
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 15; ++c) acc = fma(P[r4 * 15 + c], H[m4 * 15 + c], acc);
+        PHt[tid] = acc;
+      }
+      __syncthreads();
+      if (tid < 16) {
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 15; ++c) acc = fma(H[r4 * 15 + c], PHt[c * 4 + m4], acc);
+        S[tid] = acc + R[tid];
+      }
+      __syncthreads();
+      {
+        double Sl[16], Sil[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) Sl[e] = S[e];
+        inv4(Sl, Sil);
+        if (tid < 16) Si[tid] = Sil[tid];
+      }
+      __syncthreads();
+      if (tid < 60) {
+        double acc = 0.0;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc = fma(PHt[r4 * 4 + n], Si[n * 4 + m4], acc);
+        K[tid] = acc;
+      }
+      __syncthreads();
+      if (ent) {
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) acc = fma(K[rr * 4 + m], H[m * 15 + cc], acc);
+        A[tid] = (rr == cc ? 1.0 : 0.0) - acc;
+      }
+      if (tid < 60) {
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) acc = fma(K[r4 * 4 + m], R[m * 4 + m4], acc);
+        KR[tid] = acc;
+      }
+      __syncthreads();
+      if (ent) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 15; ++j) acc = fma(A[rr * 15 + j], P[j * 15 + cc], acc);
+        T[tid] = acc;
+      }
+      __syncthreads();
+      if (ent) {
+        double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 15; ++k) a1 = fma(T[rr * 15 + k], A[cc * 15 + k], a1);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) a2 = fma(KR[rr * 4 + n], K[cc * 4 + n], a2);
+        P[tid] = a1 + a2;
+      }
+      __syncthreads();
+      ++i_upd;
+    }
+    // ---- error observer: the five trigonometric values on five warps ----
+    const double dl3 = 3.0 * sqrt(fabs(P[6 * 15 + 6])), dm3 = 3.0 * sqrt(fabs(P[7 * 15 + 7])),
+                 dh3 = 3.0 * sqrt(fabs(P[8 * 15 + 8]));
+    if (slip_i + 1 < nsteps && obs_cannot_trigger(ob, dl3, dm3, dh3, cfg.thresh)) continue;   // same P in every thread
+    const double lat3 = lat + dl3;
+    const double lon3 = lon + dm3;
+    const double h3 = hgt + dh3;
+    if ((tid & 31) == 0) {
+      const int wv = tid >> 5;
+      if (wv == 0) trig5[0] = sin(lat3);
+      else if (wv == 1) trig5[1] = cos(lat3);
+      else if (wv == 2) trig5[2] = tan(lat3);
+      else if (wv == 3) trig5[3] = sin(lon3);
+      else if (wv == 4) trig5[4] = cos(lon3);
+    }
+    __syncthreads();
+    double enu3[3];
+    llh_to_enu_trig(trig5[0], trig5[1], trig5[2], trig5[3], trig5[4], h3, lk, cfg, enu3);
+    const double dx = enu3[0] - enu0[0], dy = enu3[1] - enu0[1];
+    xy = sqrt(dx * dx + dy * dy);
+    if (xy > cfg.thresh) { trig = 1; step = slip_i; break; }
+  }
+  if (tid == 0) {
     a.triggered[b] = trig;
     a.i_stop[b] = i_upd;
     a.step_stop[b] = step;
@@ -385,6 +585,12 @@ extern "C" int cngp_launch_lookahead(const double* mean, const double* sigma, lo
   if (!attr_set) {
     cudaFuncSetAttribute(zupt_lookahead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
+  }
+  const char* force = getenv("CNGP_LOOKAHEAD_KERNEL");     // "warp" / "cta": tests exercise both on the same batch
+  const bool cta = force ? force[0] == 'c' : B <= LA_CTA_MAX_B;
+  if (cta) {
+    zupt_lookahead_cta_kernel<<<(unsigned)B, LA_CTA_THREADS, LA_WS * sizeof(double), stream>>>(a);
+    return (int)cudaGetLastError();
   }
   const long long grid = (B + LA_WARPS - 1) / LA_WARPS;
   zupt_lookahead_kernel<<<(unsigned)grid, LA_WARPS * 32, smem, stream>>>(a);

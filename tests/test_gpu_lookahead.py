@@ -87,3 +87,37 @@ def test_lookahead_fix_h_packing_and_ratio(gp_ctx):
         ref = so.lookahead_batch(mean, sigma, ctx["P"], ctx["Q"], ctx["STM"], hv, ctx["pos"], cfg_o)
         for k in ("triggered", "i_stop", "step_stop"):
             assert np.array_equal(out[k], ref[k]), (k, ratio)
+
+
+@pytest.mark.parametrize("kernel", ["warp", "cta"])
+def test_both_kernel_shapes_match_the_oracle(gp_ctx, monkeypatch, kernel):
+    """Large batches run one warp per window, small ones (<= 592 windows, the reference's single callback) one CTA per
+    window; both keep the oracle's fma order, so the decisions - and the two kernels' xy_err - are identical."""
+    monkeypatch.setenv("CNGP_LOOKAHEAD_KERNEL", kernel)
+    B, M = 96, 260
+    mean, sigma = gp_outputs(B, M, seed=5)
+    ctx = syn.lookahead_context(syn.window_sigmas(50, B, lo=0.3, hi=0.9))
+    out = gp_ctx.zupt_lookahead(mean, sigma, ctx["P"], ctx["Q"], ctx["STM"], ctx["Hvec"], ctx["pos"])
+    ref = so.lookahead_batch(mean, sigma, ctx["P"], ctx["Q"], ctx["STM"], ctx["Hvec"], ctx["pos"])
+    assert 0 < ref["triggered"].sum()
+    for k in ("triggered", "i_stop", "step_stop"):
+        assert np.array_equal(out[k], ref[k]), k
+    assert np.max(np.abs(out["xy_err"] - ref["xy_err"]) / np.maximum(1, np.abs(ref["xy_err"]))) < 1e-9
+    monkeypatch.setenv("CNGP_LOOKAHEAD_KERNEL", "cta" if kernel == "warp" else "warp")
+    other = gp_ctx.zupt_lookahead(mean, sigma, ctx["P"], ctx["Q"], ctx["STM"], ctx["Hvec"], ctx["pos"])
+    assert np.array_equal(out["xy_err"], other["xy_err"]) and np.array_equal(out["step_stop"], other["step_stop"])
+
+
+def test_dense_stm_takes_the_general_propagation(gp_ctx, monkeypatch):
+    """An STM whose bias rows are not unit rows disables the copy shortcut (both kernels)."""
+    B, M = 8, 60
+    mean, sigma = gp_outputs(B, M, seed=9)
+    ctx = syn.lookahead_context(0.6)
+    F = ctx["STM"].reshape(15, 15).copy()
+    F[10, 2] = 1e-4                                        # couples a bias state: rows 9..14 are no longer unit rows
+    ref = so.lookahead_batch(mean, sigma, ctx["P"], ctx["Q"], F.reshape(225), ctx["Hvec"], ctx["pos"])
+    for kernel in ("warp", "cta"):
+        monkeypatch.setenv("CNGP_LOOKAHEAD_KERNEL", kernel)
+        out = gp_ctx.zupt_lookahead(mean, sigma, ctx["P"], ctx["Q"], F.reshape(225), ctx["Hvec"], ctx["pos"])
+        for k in ("triggered", "i_stop", "step_stop"):
+            assert np.array_equal(out[k], ref[k]), (kernel, k)

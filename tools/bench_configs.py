@@ -145,8 +145,16 @@ def single(ctx):
     for _ in range(20):
         out = cb()
     dt = (time.perf_counter() - t0) / 20
+    ctx.set_profiling(True)
+    for k in range(6):
+        ctx.profile_read(k, reset=True)
+    for _ in range(5):
+        cb()
+    prof = {name: ctx.profile_read(k)[0] / 5 for k, name in ((0, "fit"), (1, "var"), (3, "lookahead"))}
+    ctx.set_profiling(False)
     return {"config": "configs[0] single window N=100, SE, predict + look-ahead, host buffers", "ms_per_callback": dt * 1e3,
-            "triggered": int(out["triggered"][0]), "i_stop": int(out["i_stop"][0])}
+            "kernel_ms": prof, "triggered": int(out["triggered"][0]), "i_stop": int(out["i_stop"][0]),
+            "step_stop": int(out["step_stop"][0])}
 
 
 def recorder(ctx, scale):
