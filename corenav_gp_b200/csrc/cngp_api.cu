@@ -409,7 +409,7 @@ struct Stage {
 // ------------------------------------------------------------------------------------------------------------
 template <int NT_MAX, int G, int WG, int NSLOT, int CT, int KID>
 static int launch_var_k(cngp_ctx* ctx, VarArgs& va, long long nwin, cudaStream_t s) {
-  const long long nrounds = (va.mt + WG - 1) / WG;
+  const long long nrounds = (va.mt - va.mt0 + WG - 1) / WG;
   const long long units = nwin * nrounds;
   const long long grid = std::min<long long>((units + G - 1) / G, g_sm_count);   // persistent: one CTA per SM
   const size_t smem = var_smem_bytes(G, WG, NSLOT, CT);
@@ -538,7 +538,7 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
       va.kp = kp;
       va.theta = d_theta; va.theta_stride = theta_stride; va.theta_mode = theta_stride ? 1 : 0;
       va.xstar = d_xs; va.xstar_stride = xstar_stride;
-      va.N = N; va.nt = nt; va.M = M; va.mt = mt; va.window0 = w0; va.n_windows_launch = nw;
+      va.N = N; va.nt = nt; va.M = M; va.mt = mt; va.mt0 = 0; va.window0 = w0; va.n_windows_launch = nw;
       va.L = Lbuf; va.z = zbuf; va.feat = fbuf; va.status = d_status; va.mean = d_mean; va.var = d_var;
       va.sigma_mode = sigma_mode;
       va.kstage = nullptr;
@@ -551,6 +551,17 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
       else if (getenv("CNGP_VAR_VARIANT") && atoi(getenv("CNGP_VAR_VARIANT")) == 2) vrc = launch_var<32, 1, 12, 6, 32>(ctx, kid, va, nw, ctx->stream);
       else if (getenv("CNGP_VAR_VARIANT") && atoi(getenv("CNGP_VAR_VARIANT")) == 3) vrc = launch_var<32, 1, 12, 8, 16>(ctx, kid, va, nw, ctx->stream);
 #endif
+      else if (mt > 12 && mt % 12 >= 1 && mt % 12 <= 3) {
+        // A round of 12 test tiles streams the factor once; a last round of 1..3 tiles would stream it for a quarter of
+        // the warps.  Those tiles go to a second launch in which every CTA runs four groups of three warps, each
+        // streaming the factor of a different window, so all twelve warps stay busy.
+        va.mt = mt - mt % 12;
+        vrc = launch_var<32, 1, 12, 3, 64>(ctx, kid, va, nw, ctx->stream);
+        ctx->end();
+        ctx->begin(CNGP_PROF_VAR);
+        va.mt0 = va.mt; va.mt = mt;
+        if (!vrc) vrc = launch_var<32, 4, 3, 3, 16>(ctx, kid, va, nw, ctx->stream);
+      }
       else vrc = launch_var<32, 1, 12, 3, 64>(ctx, kid, va, nw, ctx->stream);
       ctx->end();
       if (vrc) return fail(ctx, vrc, "predict: staging buffer for the generic kernel path");

@@ -42,7 +42,8 @@ struct VarArgs {
   int theta_mode;          // 0 shared, 1 per window
   const double* xstar;     // [n_windows][M] or [M]
   long long xstar_stride;  // M or 0
-  int N, nt, M, mt;        // mt = ceil(M / 8)
+  int N, nt, M, mt;        // mt = ceil(M / 8): test tiles [mt0, mt) are handled by this launch
+  int mt0;
   long long window0;       // first window of this launch
   long long n_windows_launch;
   const double* L;         // [chunk][tiles][64]  (phase A output; one chunk of slack before the first window)
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(G * WG * 32, 1) gp_var_kernel(const VarArgs a)
   const int n_tiles = tiles_in_lower(nt);
   const int ce_max = (n_tiles - 1) / VAR_CT;      // chunk ids count from the END of a window's factor
   const int nchunks = ce_max + 1;
-  const int nrounds = (mt + WG - 1) / WG;
+  const int nrounds = (mt - a.mt0 + WG - 1) / WG;
   const long long n_units = a.n_windows_launch * nrounds;
   const long long unit_stride = (long long)gridDim.x * G;
   const long long unit0 = (long long)blockIdx.x * G + grp;
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(G * WG * 32, 1) gp_var_kernel(const VarArgs a)
     const int round = (int)(u - lw * nrounds);
     const long long win = a.window0 + lw;
     const double* th = a.theta + (a.theta_mode == 0 ? 0 : win) * a.theta_stride;
-    const int m8 = round * WG + wg;
+    const int m8 = a.mt0 + round * WG + wg;
     int slot = g % NSLOT;
     uint32_t parity = (uint32_t)(g / NSLOT) & 1u;
     int gc = g, duty = g % WG;     // running chunk index of this warp; warp (gc mod WG) has refill duty at chunk gc
