@@ -790,11 +790,11 @@ extern "C" int cngp_slip_record_batch(cngp_ctx* ctx, const double* joint, const 
   int* d_nw = (int*)st.out(n_windows, sizeof(int) * (size_t)B);
   if (st.err) return fail(ctx, st.err, "slip_record: staging failed");
   // windows that never close and samples never recorded read as zero
-  cudaMemsetAsync(d_ta, 0, sizeof(double) * bw * cap, ctx->stream);
-  cudaMemsetAsync(d_sa, 0, sizeof(double) * bw * cap, ctx->stream);
-  cudaMemsetAsync(d_ns, 0, sizeof(int) * bw, ctx->stream);
-  cudaMemsetAsync(d_pu, 0, sizeof(int) * bw, ctx->stream);
-  cudaMemsetAsync(d_su, 0xff, sizeof(int) * bw, ctx->stream);
+  CU(ctx, cudaMemsetAsync(d_ta, 0, sizeof(double) * bw * cap, ctx->stream));
+  CU(ctx, cudaMemsetAsync(d_sa, 0, sizeof(double) * bw * cap, ctx->stream));
+  CU(ctx, cudaMemsetAsync(d_ns, 0, sizeof(int) * bw, ctx->stream));
+  CU(ctx, cudaMemsetAsync(d_pu, 0, sizeof(int) * bw, ctx->stream));
+  CU(ctx, cudaMemsetAsync(d_su, 0xff, sizeof(int) * bw, ctx->stream));
   ctx->begin(CNGP_PROF_MISC);
   const int e = cngp_launch_slip_record(d_joint, d_att, d_vel, d_cmd, d_scmd, B, T, &c, max_windows, cap, d_slip, d_ta,
                                         d_sa, d_ns, d_pu, d_su, d_nw, ctx->stream);
