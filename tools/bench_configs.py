@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Device-timed numbers for the BASELINE.json configs that bench.py does not carry on its line.
 
-    python tools/bench_configs.py [sweep|mc|single|recorder|all] [scale]
+    python tools/bench_configs.py [sweep|mc|single|callback|recorder|all] [scale]
 
   sweep  - configs[2]: Kernel Selection sweep, C = 64 candidates (8 kernel families x 8 hyper-parameter draws) x
            B = 4096 windows, N = 256, LML + gradient (cngp_lml_grad_batch).
@@ -157,6 +157,26 @@ def single(ctx):
             "step_stop": int(out["step_stop"][0])}
 
 
+def callback_fit(ctx):
+    """Rows a1-a7 end to end, as the reference runs them: the node callback with the hyper-parameter fit (L-BFGS-B from
+    all-ones on softplus parameters, gp_slip_node.py:31-36), n = 149 samples (134 training points), 600-step horizon."""
+    out = {}
+    for B in (1, 64):
+        rows = []
+        for b in range(B):
+            t = 21.0 + np.arange(149)
+            rng = np.random.default_rng(100 + b)
+            rows.append((t, 0.02 + 0.05 * np.sin(2 * np.pi * np.arange(149) / 37.0) + 0.03 * rng.standard_normal(149)))
+        t = np.stack([r[0] for r in rows]); s = np.stack([r[1] for r in rows])
+        ctx.gp_slip("rbf*brownian", t, s)
+        t0 = time.perf_counter()
+        mean, sigma, status = ctx.gp_slip("rbf*brownian", t, s)
+        dt = time.perf_counter() - t0
+        out[f"B={B}"] = {"ms_per_call": dt * 1e3, "ms_per_window": dt * 1e3 / B, "ok": bool((status >= 0).all()),
+                         "m": int(mean.shape[1])}
+    return {"config": "node callback with hyper-parameter fit (rbf*brownian, n=149, horizon 600), host buffers", **out}
+
+
 def recorder(ctx, scale):
     """Row N1: slip extraction + recorder, 65536 drives x 512 updates resident in HBM (104 algorithmic bytes/update)."""
     B, T = max(256, int(65536 * scale)), 512
@@ -197,6 +217,8 @@ def main():
         lines.append(single(ctx))
     if what in ("sweep", "all") and rank == 0:
         lines.append(sweep(ctx, scale))
+    if what in ("callback", "all") and rank == 0:
+        lines.append(callback_fit(ctx))
     if what in ("recorder", "all") and rank == 0:
         lines.append(recorder(ctx, scale))
     if what in ("mc", "all"):
