@@ -186,6 +186,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
   }
   __syncthreads();
 
+  const bool full_window = N == 8 * nt;
   auto feat_at = [&](int i) -> PointFeat {
     if (KID == KID_GENERIC) return PointFeat{fx[i], 0.0, 0.0, 0.0};
     if (KID == KID_RBF_PER) return PointFeat{fx[i], fxx[i], fc[i], fs[i]};
@@ -208,6 +209,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
     }
     const int c0 = 8 * c + 2 * q, c1 = c0 + 1, row = 8 * i + r;
     const PointFeat fr = feat_at(row), f0 = feat_at(c0), f1 = feat_at(c1);
+    if (KID != KID_GENERIC && full_window && i != c)   // interior tile of an unpadded window: no diagonal, no padding
+      return tile2{fk.eval_tab(fr, f0, false, etab), fk.eval_tab(fr, f1, false, etab)};
     double v0 = ky_entry(row, c0, fr, f0), v1 = ky_entry(row, c1, fr, f1);
     if (row == c0 && row < N) v0 += dadd;
     if (row == c1 && row < N) v1 += dadd;
