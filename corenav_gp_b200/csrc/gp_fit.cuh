@@ -137,7 +137,7 @@ template <int KID, int NW, int T>
 __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_kernel(const FitArgs a) {
   constexpr int FIT_THREADS = (NW + 1) * 32;
   extern __shared__ __align__(128) double pool[];               // tile pool, see fit_pool_tiles
-  __shared__ double fx[NPAD], fxx[NPAD], fc[NPAD], fs[NPAD];   // per-point features
+  __shared__ __align__(16) double fx[NPAD], fxx[NPAD], fc[NPAD], fs[NPAD];   // per-point features
   __shared__ double ys[NPAD];
   __shared__ __align__(16) double zs[NPAD];
   __shared__ LeafConst hc[CNGP_MAX_LEAVES];
@@ -208,9 +208,15 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
       return tile2{av.x, av.y};
     }
     const int c0 = 8 * c + 2 * q, c1 = c0 + 1, row = 8 * i + r;
+    if (KID != KID_GENERIC && full_window && i != c) {   // interior tile of an unpadded window: no diagonal, no padding
+      const PointFeat fr = feat_at(row);
+      const double2 x2 = *reinterpret_cast<const double2*>(fx + c0), xx2 = *reinterpret_cast<const double2*>(fxx + c0);
+      double2 c2 = make_double2(0.0, 0.0), s2 = make_double2(0.0, 0.0);
+      if (KID == KID_RBF_PER) { c2 = *reinterpret_cast<const double2*>(fc + c0); s2 = *reinterpret_cast<const double2*>(fs + c0); }
+      return tile2{fk.eval_tab(fr, PointFeat{x2.x, xx2.x, c2.x, s2.x}, false, etab),
+                   fk.eval_tab(fr, PointFeat{x2.y, xx2.y, c2.y, s2.y}, false, etab)};
+    }
     const PointFeat fr = feat_at(row), f0 = feat_at(c0), f1 = feat_at(c1);
-    if (KID != KID_GENERIC && full_window && i != c)   // interior tile of an unpadded window: no diagonal, no padding
-      return tile2{fk.eval_tab(fr, f0, false, etab), fk.eval_tab(fr, f1, false, etab)};
     double v0 = ky_entry(row, c0, fr, f0), v1 = ky_entry(row, c1, fr, f1);
     if (row == c0 && row < N) v0 += dadd;
     if (row == c1 && row < N) v1 += dadd;
