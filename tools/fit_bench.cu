@@ -83,6 +83,8 @@ int main(int argc, char** argv) {
   fa.L = dL; fa.z = dz; fa.feat = dfeat; fa.lml = dlml; fa.status = dst;
   printf("gp_fit_kernel<rbf+stdperiodic>  windows %d  N %d\n", B, N);
   run<8, 4>("8x4", fa, B, dlml, ddbg);
+  run<10, 4>("10x4", fa, B, dlml, ddbg);
+  run<9, 4>("9x4", fa, B, dlml, ddbg);
   run<11, 3>("11x3", fa, B, dlml, ddbg);
   run<12, 3>("12x3", fa, B, dlml, ddbg);
   run<16, 2>("16x2", fa, B, dlml, ddbg);
