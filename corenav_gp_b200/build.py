@@ -85,8 +85,8 @@ HOST_LIB = os.path.join(HERE, "libgp_predictor_b200.so")
 
 def build_host() -> str:
     """The C++ host side above the C ABI: the ROS-free GpPredictor class (include/gp_predictor_b200.hpp)."""
-    src = os.path.join(HERE, "host", "gp_predictor.cpp")
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", HOST_LIB, src, LIB, "-Wl,-rpath,$ORIGIN"]
+    srcs = [os.path.join(HERE, "host", "gp_predictor.cpp"), os.path.join(HERE, "host", "gp_slip_predict.cpp")]
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", HOST_LIB, *srcs, LIB, "-Wl,-rpath,$ORIGIN"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -99,4 +99,12 @@ class GpPredictor {
   void sync_init();
 };
 
+// The GP node's callback for a C++ caller (core_navigation/script/gp_slip_node.py:16-63, rows a1-a7): train on the first
+// int(0.9 n) samples, fit the hyper-parameters from all-ones (theta == nullptr, as m.optimize() does) or take them as
+// given (noise last), predict on arange(min(time), max(time) + horizon, 1) and return mean[n:], sigma = 2 sqrt(var[n:]).
+// Throws std::runtime_error with the library's message when the window cannot be processed (GPy would raise).
+// Implemented in corenav_gp_b200/host/gp_slip_predict.cpp (libgp_predictor_b200.so).
+core_nav::GP_Output gp_slip_predict(cngp_ctx* ctx, const core_nav::GP_Input& data, const char* kernel = "rbf*brownian",
+                                    const double* theta = nullptr, int horizon = 600);
+
 #endif  // GP_PREDICTOR_B200_HPP_

@@ -85,3 +85,55 @@ def test_gp_predictor_host_logic_cpu(tmp_path):
 @pytest.mark.gpu
 def test_gp_predictor_on_gpu(tmp_path):
     check_against_oracle(build_cli(fake=False), tmp_path)
+
+
+def build_slip_cli() -> str:
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "gp_slip_cli")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "host", "gp_slip_cli.cpp"),
+                           os.path.join(ROOT, "corenav_gp_b200", "host", "gp_slip_predict.cpp"),
+                           os.path.join(ROOT, "corenav_gp_b200", "libcngp.so"),
+                           "-Wl,-rpath," + os.path.join(ROOT, "corenav_gp_b200")])
+    return exe
+
+
+def test_gp_slip_predict_is_exported_and_links():
+    """CPU: the C++ mirror of the node callback (gp_slip_node.py:16-63) is part of libgp_predictor_b200.so and the driver
+    links against the C ABI (no compute: there is no GPU here)."""
+    from corenav_gp_b200 import build
+    lib = build.build_host()
+    syms = subprocess.run(["nm", "-DC", lib], capture_output=True, text=True).stdout
+    assert "gp_slip_predict(cngp_ctx*, core_nav::GP_Input const&, char const*, double const*, int)" in syms
+    assert os.path.exists(build_slip_cli())
+
+
+def slip_window(n=149, seed=0):
+    rng = np.random.default_rng(seed)
+    t = 21.0 + np.arange(n)
+    return t, 0.02 + 0.05 * np.sin(2 * np.pi * np.arange(n) / 37.0) + 0.03 * rng.standard_normal(n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fit", [False, True])
+def test_gp_slip_predict_matches_the_python_node(gp_ctx, tmp_path, fit):
+    """GPU: gp_slip_predict (C++) and corenav_gp_b200.gp_slip_node / GpContext.gp_slip (Python) are the same ABI call -
+    identical bits - and the fixed-hyper-parameter result is the oracle's callback to 1e-9."""
+    from oracle import gp_oracle as go
+    exe = build_slip_cli()
+    t, s = slip_window()
+    src, dst = tmp_path / "in.bin", tmp_path / "out.bin"
+    np.concatenate([[float(t.size)], t, s]).tofile(src)
+    r = subprocess.run([exe, str(src), str(dst)] + (["fit"] if fit else []), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert json.loads(r.stdout.strip().splitlines()[-1])["seq"] == 7
+    out = np.fromfile(dst)
+    m = int(out[0])
+    mean, sigma = out[1:1 + m], out[1 + m:1 + 2 * m]
+    theta = None if fit else np.array([0.01, 10.0, 0.05, 1e-3])
+    pm, ps, st = gp_ctx.gp_slip("rbf*brownian", t[None], s[None], theta=theta)
+    assert st[0] >= 0 and pm.shape[1] == m == 599
+    assert np.array_equal(pm[0], mean) and np.array_equal(ps[0], sigma)
+    if not fit:
+        rm, rs = go.gp_slip_callback(t, s, go.KernelExpr("rbf*brownian"), theta=theta[:-1], noise=theta[-1])
+        assert np.max(np.abs(mean - rm) / np.maximum(1, np.abs(rm))) < 1e-9
+        assert np.max(np.abs(sigma - rs) / np.maximum(1, np.abs(rs))) < 1e-9
