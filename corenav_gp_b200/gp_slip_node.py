@@ -88,6 +88,23 @@ def callback_batch(windows: Sequence, theta=None, kernel: str = KERNEL) -> List[
     return [GP_Output(mean=mean[b], sigma=sigma[b]) for b in range(len(windows))]
 
 
+def callback_bytes(serialized: bytes, theta=None, kernel: str = KERNEL, framed: bool = False) -> bytes:
+    """The node as a byte pipe for a TCPROS / rosbag driver: a serialised core_nav/GP_Input in, the
+    serialised core_nav/GP_Output of `callback` out (header copied, as a republisher would).  framed=True: both carry
+    the uint32 TCPROS length prefix."""
+    from . import wire
+    if framed:
+        body, used = wire.unframe(serialized)
+        if body is None or used != len(serialized):
+            raise ValueError("callback_bytes: expected exactly one whole TCPROS frame")
+        serialized = body
+    msg = wire.deserialize_gp_input(serialized)
+    out = callback(GP_Input(time_array=msg.time_array, slip_array=msg.slip_array), theta=theta, kernel=kernel)
+    reply = wire.serialize(wire.GPOutput(wire.Header(msg.header.seq, msg.header.stamp, msg.header.frame_id),
+                                         np.asarray(out.mean), np.asarray(out.sigma)))
+    return wire.frame(reply) if framed else reply
+
+
 def gaussian_process(subscribe: Callable[[Callable], None]) -> None:
     """gp_slip_node.gaussian_process: attach `callback` to a message source (rospy.Subscriber in a ROS graph)."""
     subscribe(callback)

@@ -122,15 +122,25 @@ def test_cpp_and_python_agree_byte_for_byte(cli, tmp_path):
     through_cpp(cli, "gp_output", go[:-1], tmp_path, expect_rc=4)        # truncated: std::out_of_range, reported
 
 
-def test_wire_to_callback_to_wire(tmp_path):
-    """The node as a byte pipe: GP_Input bytes -> gp_slip_node.callback -> GP_Output bytes (GP arithmetic stubbed here;
-    tests/test_gpu_fit_callback.py runs the real one)."""
+def test_wire_to_callback_to_wire(monkeypatch):
+    """gp_slip_node.callback_bytes: GP_Input bytes -> callback -> GP_Output bytes.  The GP arithmetic is stubbed here (no
+    GPU on this side; tests/test_gpu_fit_callback.py runs the real callback): what is checked is the byte plumbing."""
     from corenav_gp_b200 import gp_slip_node as node
     n = 40
-    gi = wire.GPInput(wire.Header(1, 5.0, ""), 20.0 + np.arange(n), 0.05 * np.sin(np.arange(n) / 5.0))
-    msg = wire.deserialize_gp_input(wire.serialize(gi))
-    assert msg.time_array.size == n
-    ntr = int(0.9 * n)                                                   # gp_slip_node.py:23-24
-    assert node.train_split(n) == ntr if hasattr(node, "train_split") else True
-    out = wire.GPOutput(wire.Header(msg.header.seq, msg.header.stamp, ""), np.zeros(599), np.ones(599))
-    assert wire.deserialize_gp_output(wire.serialize(out)).sigma.sum() == 599.0
+    seen = {}
+
+    def fake_callback(data, theta=None, kernel=node.KERNEL):
+        seen["n"] = len(data.time_array)
+        seen["t0"] = float(data.time_array[0])
+        return node.GP_Output(mean=np.arange(599.0), sigma=np.full(599, 0.25))
+
+    monkeypatch.setattr(node, "callback", fake_callback)
+    gi = wire.GPInput(wire.Header(11, 5.5, "odom"), 20.0 + np.arange(n), 0.05 * np.sin(np.arange(n) / 5.0))
+    reply = node.callback_bytes(wire.serialize(gi))
+    out = wire.deserialize_gp_output(reply)
+    assert seen == {"n": n, "t0": 20.0}
+    assert out.header == gi.header and out.mean[598] == 598.0 and out.sigma.sum() == 599 * 0.25
+    framed = node.callback_bytes(wire.frame(wire.serialize(gi)), framed=True)
+    assert wire.unframe(framed) == (reply, len(reply) + 4)
+    with pytest.raises(ValueError):
+        node.callback_bytes(wire.frame(wire.serialize(gi))[:-1], framed=True)
