@@ -34,6 +34,37 @@ struct LlhConst {
   double Rm[3][3];              // ECEF -> ENU rotation at init_llh
 };
 
+// Deterministic sin / cos: Cody-Waite reduction by pi/2 in three fma steps, then the classic degree-13 / 14 minimax
+// polynomials on [-pi/4, pi/4] as fma Horner chains.  Only IEEE-exact operations in a fixed order (this TU is built with
+// -fmad=false), so the C oracle (oracle/stop_oracle.c, trig_mode = 1, built with -ffp-contract=off) returns the same bits
+// and the stop decision is reproducible at a 0-ulp margin; within 1 ulp of libm / libdevice.  tan = sin / cos.
+__device__ __forceinline__ void det_sincos(double x, double& sn, double& cs) {
+  const double k = rint(x * 6.36619772367581382433e-01);
+  double r = fma(-k, 1.57079632679489655800e+00, x);
+  r = fma(-k, 6.12323399573676603587e-17, r);
+  r = fma(-k, -1.49738490485916983000e-33, r);
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = fma(ps, z, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  const double s = fma(r * z, ps, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, z, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double hz = 0.5 * z;
+  const double w = 1.0 - hz;
+  const double c = w + (((1.0 - w) - hz) + (z * z) * pc);
+  const long long q = (long long)k & 3;
+  sn = (q == 0) ? s : (q == 1) ? c : (q == 2) ? -s : -c;
+  cs = (q == 0) ? c : (q == 1) ? -s : (q == 2) ? -c : s;
+}
+
 __device__ __forceinline__ LlhConst llh_prepare(const cngp_stop_config& c) {
   LlhConst k;
   const double a = 6378137.0000, b = 6356752.3142;
@@ -41,8 +72,9 @@ __device__ __forceinline__ LlhConst llh_prepare(const cngp_stop_config& c) {
   const double e = sqrt(1 - boa * boa);
   k.e2 = e * e;
   k.one_m_e2 = 1 - e * e;
-  const double sinPhi = sin(c.init_llh[0]), cosPhi = cos(c.init_llh[0]);
-  const double sinLam = sin(c.init_llh[1]), cosLam = cos(c.init_llh[1]);
+  double sinPhi, cosPhi, sinLam, cosLam;
+  det_sincos(c.init_llh[0], sinPhi, cosPhi);
+  det_sincos(c.init_llh[1], sinLam, cosLam);
   k.Rm[0][0] = -1 * sinLam; k.Rm[0][1] = cosLam; k.Rm[0][2] = 0;
   k.Rm[1][0] = (-1 * sinPhi) * cosLam; k.Rm[1][1] = (-1 * sinPhi) * sinLam; k.Rm[1][2] = cosPhi;
   k.Rm[2][0] = cosPhi * cosLam; k.Rm[2][1] = cosPhi * sinLam; k.Rm[2][2] = sinPhi;
@@ -72,7 +104,10 @@ __device__ __forceinline__ void llh_to_enu_trig(double sinphi, double cosphi, do
 
 __device__ __forceinline__ void llh_to_enu_dev(double lat, double lon, double h, const LlhConst& k,
                                                const cngp_stop_config& c, double enu[3]) {
-  llh_to_enu_trig(sin(lat), cos(lat), tan(lat), sin(lon), cos(lon), h, k, c, enu);
+  double sp, cp, sl, cl;
+  det_sincos(lat, sp, cp);
+  det_sincos(lon, sl, cl);
+  llh_to_enu_trig(sp, cp, sp / cp, sl, cl, h, k, c, enu);
 }
 
 // closed-form 4x4 inverse through 2x2 minors (Eigen's fixed-size inverse at gp_predictor.cpp:90 is the same math)
@@ -166,7 +201,7 @@ __device__ __forceinline__ bool obs_cannot_trigger(const ObsBound& o, double dl,
 
 // per-warp shared-memory working set (doubles)
 constexpr int LA_P = 0, LA_T = 225, LA_A = 450, LA_PHT = 675, LA_K = 735, LA_KR = 795, LA_S = 855, LA_SI = 871,
-              LA_R = 887, LA_F = 903, LA_Q = 1128, LA_H = 1353, LA_WS = 1413 + 3;  // padded to an even count
+              LA_R = 887, LA_F = 903, LA_Q = 1128, LA_H = 1353, LA_HP = 1413, LA_WS = 1473 + 3;  // padded to an even count
 
 __global__ void __launch_bounds__(LA_WARPS * 32) zupt_lookahead_kernel(const LookaheadArgs a) {
   extern __shared__ double smem[];
@@ -175,7 +210,7 @@ __global__ void __launch_bounds__(LA_WARPS * 32) zupt_lookahead_kernel(const Loo
   if (b >= a.B) return;
   double* ws = smem + (long long)w * LA_WS;
   double *P = ws + LA_P, *T = ws + LA_T, *A = ws + LA_A, *PHt = ws + LA_PHT, *K = ws + LA_K, *KR = ws + LA_KR,
-         *S = ws + LA_S, *Si = ws + LA_SI, *R = ws + LA_R, *F = ws + LA_F, *Q = ws + LA_Q, *H = ws + LA_H;
+         *S = ws + LA_S, *Si = ws + LA_SI, *R = ws + LA_R, *F = ws + LA_F, *Q = ws + LA_Q, *H = ws + LA_H, *HP = ws + LA_HP;
   const cngp_stop_config& cfg = a.cfg;
   const int pw = a.per_window;
   const double* gP = a.P + ((pw & CNGP_PERWIN_P) ? b * 225 : 0);
@@ -291,12 +326,20 @@ __global__ void __launch_bounds__(LA_WARPS * 32) zupt_lookahead_kernel(const Loo
         for (int c = 0; c < 15; ++c) acc = fma(P[rr * 15 + c], H[mm * 15 + c], acc);
         PHt[idx] = acc;
       }
+      // S = (H P) H' + R: H_*P_pred*H_.transpose() is parsed left to right (gp_predictor.cpp:90)
+      for (int idx = lane; idx < 60; idx += 32) {
+        const int mm = idx / 15, c = idx % 15;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 15; ++j) acc = fma(H[mm * 15 + j], P[j * 15 + c], acc);
+        HP[idx] = acc;
+      }
       __syncwarp();
       if (lane < 16) {
         const int mm = lane / 4, nn = lane % 4;
         double acc = 0.0;
 #pragma unroll
-        for (int c = 0; c < 15; ++c) acc = fma(H[mm * 15 + c], PHt[c * 4 + nn], acc);
+        for (int c = 0; c < 15; ++c) acc = fma(HP[mm * 15 + c], H[nn * 15 + c], acc);
         S[lane] = acc + R[lane];
       }
       __syncwarp();
@@ -363,22 +406,18 @@ __global__ void __launch_bounds__(LA_WARPS * 32) zupt_lookahead_kernel(const Loo
       __syncwarp();
       ++i_upd;
     }
-    // ---- error observer: the five trigonometric values are spread over lanes 0..4 ----
+    // ---- error observer ----
     const double dl3 = 3.0 * sqrt(fabs(P[6 * 15 + 6])), dm3 = 3.0 * sqrt(fabs(P[7 * 15 + 7])),
                  dh3 = 3.0 * sqrt(fabs(P[8 * 15 + 8]));
     if (slip_i + 1 < nsteps && obs_cannot_trigger(ob, dl3, dm3, dh3, cfg.thresh)) continue;
     const double lat3 = lat + dl3;
     const double lon3 = lon + dm3;
     const double h3 = hgt + dh3;
-    double tv = 0.0;
-    if (lane == 0) tv = sin(lat3);
-    else if (lane == 1) tv = cos(lat3);
-    else if (lane == 2) tv = tan(lat3);
-    else if (lane == 3) tv = sin(lon3);
-    else if (lane == 4) tv = cos(lon3);
-    const double sp = __shfl_sync(0xffffffffu, tv, 0), cp = __shfl_sync(0xffffffffu, tv, 1),
-                 tp = __shfl_sync(0xffffffffu, tv, 2), sl = __shfl_sync(0xffffffffu, tv, 3),
-                 cl = __shfl_sync(0xffffffffu, tv, 4);
+    double tsn, tcs;                               // lane 0: latitude, lane 1: longitude
+    det_sincos(lane == 0 ? lat3 : lon3, tsn, tcs);
+    const double sp = __shfl_sync(0xffffffffu, tsn, 0), cp = __shfl_sync(0xffffffffu, tcs, 0),
+                 sl = __shfl_sync(0xffffffffu, tsn, 1), cl = __shfl_sync(0xffffffffu, tcs, 1);
+    const double tp = sp / cp;
     double enu3[3];
     llh_to_enu_trig(sp, cp, tp, sl, cl, h3, lk, cfg, enu3);
     const double dx = enu3[0] - enu0[0], dy = enu3[1] - enu0[1];
@@ -403,11 +442,10 @@ constexpr long long LA_CTA_MAX_B = 592;   // 4 windows per SM
 
 __global__ void __launch_bounds__(LA_CTA_THREADS) zupt_lookahead_cta_kernel(const LookaheadArgs a) {
   extern __shared__ double ws[];
-  __shared__ double trig5[5];
   const int tid = threadIdx.x;
   const long long b = blockIdx.x;
   double *P = ws + LA_P, *T = ws + LA_T, *A = ws + LA_A, *PHt = ws + LA_PHT, *K = ws + LA_K, *KR = ws + LA_KR,
-         *S = ws + LA_S, *Si = ws + LA_SI, *R = ws + LA_R, *F = ws + LA_F, *Q = ws + LA_Q, *H = ws + LA_H;
+         *S = ws + LA_S, *Si = ws + LA_SI, *R = ws + LA_R, *F = ws + LA_F, *Q = ws + LA_Q, *H = ws + LA_H, *HP = ws + LA_HP;
   const cngp_stop_config& cfg = a.cfg;
   const int pw = a.per_window;
   const double* gP = a.P + ((pw & CNGP_PERWIN_P) ? b * 225 : 0);
@@ -478,12 +516,18 @@ __global__ void __launch_bounds__(LA_CTA_THREADS) zupt_lookahead_cta_kernel(cons
 #pragma unroll
         for (int c = 0; c < 15; ++c) acc = fma(P[r4 * 15 + c], H[m4 * 15 + c], acc);
         PHt[tid] = acc;
+      } else if (tid >= 64 && tid < 124) {      // S = (H P) H' + R, left to right as gp_predictor.cpp:90 parses
+        const int e = tid - 64, mm = e / 15, c = e % 15;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 15; ++j) acc = fma(H[mm * 15 + j], P[j * 15 + c], acc);
+        HP[e] = acc;
       }
       __syncthreads();
       if (tid < 16) {
         double acc = 0.0;
 #pragma unroll
-        for (int c = 0; c < 15; ++c) acc = fma(H[r4 * 15 + c], PHt[c * 4 + m4], acc);
+        for (int c = 0; c < 15; ++c) acc = fma(HP[r4 * 15 + c], H[m4 * 15 + c], acc);
         S[tid] = acc + R[tid];
       }
       __syncthreads();
@@ -533,24 +577,18 @@ __global__ void __launch_bounds__(LA_CTA_THREADS) zupt_lookahead_cta_kernel(cons
       __syncthreads();
       ++i_upd;
     }
-    // ---- error observer: the five trigonometric values on five warps ----
+    // ---- error observer ----
     const double dl3 = 3.0 * sqrt(fabs(P[6 * 15 + 6])), dm3 = 3.0 * sqrt(fabs(P[7 * 15 + 7])),
                  dh3 = 3.0 * sqrt(fabs(P[8 * 15 + 8]));
     if (slip_i + 1 < nsteps && obs_cannot_trigger(ob, dl3, dm3, dh3, cfg.thresh)) continue;   // same P in every thread
     const double lat3 = lat + dl3;
     const double lon3 = lon + dm3;
     const double h3 = hgt + dh3;
-    if ((tid & 31) == 0) {
-      const int wv = tid >> 5;
-      if (wv == 0) trig5[0] = sin(lat3);
-      else if (wv == 1) trig5[1] = cos(lat3);
-      else if (wv == 2) trig5[2] = tan(lat3);
-      else if (wv == 3) trig5[3] = sin(lon3);
-      else if (wv == 4) trig5[4] = cos(lon3);
-    }
-    __syncthreads();
+    double sp, cp, sl, cl;                         // cheap enough (about 40 fma) to repeat in every thread
+    det_sincos(lat3, sp, cp);
+    det_sincos(lon3, sl, cl);
     double enu3[3];
-    llh_to_enu_trig(trig5[0], trig5[1], trig5[2], trig5[3], trig5[4], h3, lk, cfg, enu3);
+    llh_to_enu_trig(sp, cp, sp / cp, sl, cl, h3, lk, cfg, enu3);
     const double dx = enu3[0] - enu0[0], dy = enu3[1] - enu0[1];
     xy = sqrt(dx * dx + dy * dy);
     if (xy > cfg.thresh) { trig = 1; step = slip_i; break; }

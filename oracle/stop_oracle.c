@@ -4,14 +4,17 @@
  * cpu_baseline / --impl reference legs of bench.py may load it.  Nothing under corenav_gp_b200/
  * links, includes or calls it.
  *
- * PARITY UNPINNED: the reference holds no test or golden vector for this path and
- * gp_predictor.cpp itself cannot be compiled here (needs <ros/ros.h>, generated core_nav/ headers and
- * Eigen - none present), so this is a plain-C restatement of
+ * PARITY PIN: the reference holds no test or golden vector for this path, so the restatement is pinned on the
+ * reference's own code: oracle/_ref compiles /root/reference/gp_predictor/src/gp_predictor.cpp UNMODIFIED against
+ * stand-in ROS / Eigen / message headers (oracle/ref_stubs/, oracle/ref_gp_predictor.py), and tests/test_ref_stop.py
+ * holds this file to it - decisions equal, xy-error trace / final P / R_IP to 1e-12 - directly and through the
+ * committed vectors tests/golden/stop_ref_golden.npz.  (Eigen and roscpp themselves are absent from the image; what
+ * the stand-ins assume is written in their headers.)  This is a plain-C restatement of
  *   /root/reference/gp_predictor/src/gp_predictor.cpp:30-46   unpack of the SetStopping response
  *   /root/reference/gp_predictor/src/gp_predictor.cpp:64-124  look-ahead loop
  *   /root/reference/gp_predictor/src/gp_predictor.cpp:144-178 llh_to_enu
  *   /root/reference/core_navigation/src/CoreNav.cpp:652-676   server-side packing (H aliasing quirk)
- * checked by closed-form known-answer tests in tests/test_oracle_stop.py.
+ * also checked by closed-form known-answer tests in tests/test_oracle_stop.py.
  *
  * Reference quirks reproduced on purpose:
  *   q1  H is read as H(r,c) = Hvec[r*4 + c] for r<4, c<15 (gp_predictor.cpp:38-42) - the aliasing
@@ -40,15 +43,61 @@ typedef struct {
   double thresh;    /* 3.00   :102 */
   int ratio;        /* 5      :64,67 (IMU steps per odometry update) */
   int fix_h_packing;/* 0 = reference behaviour */
+  int trig_mode;    /* 0 = libm sin/cos/tan (what the reference calls); 1 = the deterministic det_* below, whose
+                       operation sequence the CUDA kernel repeats bit for bit */
+  int pad_;
   double init_llh[3];   /* config/init_params.yaml:13-16 */
   double init_ecef[3];  /* config/init_params.yaml:9-12 */
 } stop_cfg;
 
 void stop_oracle_default_cfg(stop_cfg* c) {
   c->v_nom = 0.8; c->floor_a = 0.03; c->floor_b = 0.05; c->track = 0.685; c->scale = 25.0;
-  c->thresh = 3.0; c->ratio = 5; c->fix_h_packing = 0;
+  c->thresh = 3.0; c->ratio = 5; c->fix_h_packing = 0; c->trig_mode = 0; c->pad_ = 0;
   c->init_llh[0] = 0.693457963620326; c->init_llh[1] = -1.39498384275845; c->init_llh[2] = 334.993517334743;
   c->init_ecef[0] = 859153.015300000; c->init_ecef[1] = -4836303.72660000; c->init_ecef[2] = 4055378.50100000;
+}
+
+
+/* Deterministic sin / cos / tan: Cody-Waite reduction by pi/2 in three fma steps, then the classic degree-13 / 14
+ * minimax polynomials on [-pi/4, pi/4] evaluated as fma Horner chains.  Only IEEE-exact operations (fma, mul, add,
+ * div, rint) in a fixed order, so a host compiled with -ffp-contract=off and a CUDA device compiled with -fmad=false
+ * return the same bits; the result is within 2 ulp of libm for |x| < 1e5 (tests/test_oracle_stop.py).  This is what
+ * makes the ZUPT decision reproducible at a 0-ulp margin (trig_mode = 1); trig_mode = 0 keeps libm as the reference. */
+static void det_sincos(double x, double* sn, double* cs) {
+  const double k = rint(x * 6.36619772367581382433e-01);
+  double r = fma(-k, 1.57079632679489655800e+00, x);
+  r = fma(-k, 6.12323399573676603587e-17, r);
+  r = fma(-k, -1.49738490485916983000e-33, r);
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = fma(ps, z, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  const double s = fma(r * z, ps, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, z, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double hz = 0.5 * z;
+  const double w = 1.0 - hz;
+  const double c = w + (((1.0 - w) - hz) + (z * z) * pc);
+  const long long q = (long long)k & 3;
+  *sn = (q == 0) ? s : (q == 1) ? c : (q == 2) ? -s : -c;
+  *cs = (q == 0) ? c : (q == 1) ? -s : (q == 2) ? -c : s;
+}
+void stop_oracle_det_sincos(double x, double* sn, double* cs) { det_sincos(x, sn, cs); }
+
+static void trig3(double x, int mode, double* sn, double* cs, double* tn) {
+  if (mode) {
+    det_sincos(x, sn, cs);
+    *tn = *sn / *cs;
+  } else {
+    *sn = sin(x); *cs = cos(x); *tn = tan(x);
+  }
 }
 
 /* gp_predictor.cpp:144-178 */
@@ -57,8 +106,9 @@ void stop_oracle_llh_to_enu(double lat, double lon, double height, const stop_cf
   double a = 6378137.0000, b = 6356752.3142;
   double boa = b / a;
   double e = sqrt(1 - boa * boa);
-  double sinphi = sin(phi), cosphi = cos(phi), coslam = cos(lambda), sinlam = sin(lambda);
-  double tp = tan(phi);
+  double sinphi, cosphi, tp, sinlam, coslam, unused;
+  trig3(phi, c->trig_mode, &sinphi, &cosphi, &tp);
+  trig3(lambda, c->trig_mode, &sinlam, &coslam, &unused);
   double tan2phi = tp * tp;
   double tmp2 = 1 - e * e;
   double tmpden = sqrt(1 + tmp2 * tan2phi);
@@ -67,8 +117,9 @@ void stop_oracle_llh_to_enu(double lat, double lon, double height, const stop_cf
   double tmp3 = sqrt(1 - e * e * sinphi * sinphi);
   double z1 = (a * tmp2 * sinphi) / tmp3 + h * sinphi;
   double d0 = x1 - c->init_ecef[0], d1 = y1 - c->init_ecef[1], d2 = z1 - c->init_ecef[2];
-  double sinPhi = sin(c->init_llh[0]), cosPhi = cos(c->init_llh[0]);
-  double sinLam = sin(c->init_llh[1]), cosLam = cos(c->init_llh[1]);
+  double sinPhi, cosPhi, sinLam, cosLam;
+  trig3(c->init_llh[0], c->trig_mode, &sinPhi, &cosPhi, &unused);
+  trig3(c->init_llh[1], c->trig_mode, &sinLam, &cosLam, &unused);
   double R[3][3] = {{-1 * sinLam, cosLam, 0},
                     {(-1 * sinPhi) * cosLam, (-1 * sinPhi) * sinLam, cosPhi},
                     {cosPhi * cosLam, cosPhi * sinLam, sinPhi}};
@@ -159,17 +210,24 @@ static void propagate(double P[15][15], const double F[15][15], const double Q[1
 }
 
 static void joseph_update(double P[15][15], const double H[4][15], const double R[4][4]) {
-  double PHt[15][4], S[4][4], Si[4][4], K[15][4], IKH[15][15], T[15][15], KR[15][4];
+  double PHt[15][4], HP[4][15], S[4][4], Si[4][4], K[15][4], IKH[15][15], T[15][15], KR[15][4];
   for (int r = 0; r < 15; ++r)
     for (int m = 0; m < 4; ++m) {
       double acc = 0.0;
       for (int c = 0; c < 15; ++c) acc = fma(P[r][c], H[m][c], acc);
       PHt[r][m] = acc;
     }
+  /* S = (H P) H' + R: C++ parses  H_*P_pred*H_.transpose()  (gp_predictor.cpp:90) left to right */
+  for (int m = 0; m < 4; ++m)
+    for (int c = 0; c < 15; ++c) {
+      double acc = 0.0;
+      for (int j = 0; j < 15; ++j) acc = fma(H[m][j], P[j][c], acc);
+      HP[m][c] = acc;
+    }
   for (int m = 0; m < 4; ++m)
     for (int n = 0; n < 4; ++n) {
       double acc = 0.0;
-      for (int c = 0; c < 15; ++c) acc = fma(H[m][c], PHt[c][n], acc);
+      for (int c = 0; c < 15; ++c) acc = fma(HP[m][c], H[n][c], acc);
       S[m][n] = acc + R[m][n];
     }
   inv4(S, Si);

@@ -1,6 +1,7 @@
 """ctypes wrapper around oracle/stop_oracle.c (the CPU restatement of GpPredictor::GPCallBack).
 
-TEST INFRASTRUCTURE ONLY - see the header of stop_oracle.c.  PARITY UNPINNED (no reference test exists).
+TEST INFRASTRUCTURE ONLY - see the header of stop_oracle.c.  Pinned on the reference's own code through oracle/_ref
+(tests/test_ref_stop.py).
 """
 from __future__ import annotations
 
@@ -18,6 +19,7 @@ _SRC = os.path.join(_HERE, "stop_oracle.c")
 class StopCfg(C.Structure):
     _fields_ = [("v_nom", C.c_double), ("floor_a", C.c_double), ("floor_b", C.c_double), ("track", C.c_double),
                 ("scale", C.c_double), ("thresh", C.c_double), ("ratio", C.c_int), ("fix_h_packing", C.c_int),
+                ("trig_mode", C.c_int), ("pad_", C.c_int),
                 ("init_llh", C.c_double * 3), ("init_ecef", C.c_double * 3)]
 
 
@@ -53,6 +55,15 @@ def default_cfg(**over) -> StopCfg:
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def det_sincos(x):
+    """The deterministic sin/cos shared bit for bit with the CUDA kernel (trig_mode = 1)."""
+    s, c = C.c_double(), C.c_double()
+    f = lib().stop_oracle_det_sincos
+    f.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    f(float(x), C.byref(s), C.byref(c))
+    return s.value, c.value
 
 
 def llh_to_enu(lat, lon, h, cfg=None):
