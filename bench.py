@@ -386,6 +386,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu_probe"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra.configs legs (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

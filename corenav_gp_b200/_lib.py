@@ -23,7 +23,8 @@ class Kernel(C.Structure):
 
 
 class Config(C.Structure):
-    _fields_ = [("device", c_i32), ("jitter_retry", c_i32), ("scratch_bytes", c_i64), ("reserved", c_i32 * 8)]
+    _fields_ = [("device", c_i32), ("jitter_retry", c_i32), ("scratch_bytes", c_i64), ("precision", c_i32),
+                ("reserved", c_i32 * 7)]
 
 
 class StopConfig(C.Structure):
@@ -56,6 +57,7 @@ SIGNATURES = {
     "cngp_last_error": (C.c_char_p, [c_vp]),
     "cngp_sync": (C.c_int, [c_vp]),
     "cngp_set_stream": (C.c_int, [c_vp, c_vp, c_i32]),
+    "cngp_set_precision": (C.c_int, [c_vp, c_i32]),
     "cngp_launch_count": (c_i64, [c_vp]),
     "cngp_set_profiling": (C.c_int, [c_vp, c_i32]),
     "cngp_profile_read": (C.c_int, [c_vp, c_i32, C.POINTER(C.c_double), C.POINTER(c_i64), c_i32]),

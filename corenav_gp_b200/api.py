@@ -41,41 +41,49 @@ def _is_cuda(a) -> bool:
 class _Arg:
     """Pointer + keep-alive for one array argument."""
 
-    def __init__(self, a, dtype, device_mode: bool, allow_none=False):
+    def __init__(self, a, dtype, device_mode: bool, allow_none=False, output=False):
+        """Inputs are coerced (dtype, contiguity).  OUTPUTS are never coerced: the library writes through the pointer,
+        so a converted copy would leave the caller's buffer untouched - a wrong dtype or a non-contiguous output raises."""
         self.keep = None
         self.ptr = None
         if a is None:
             assert allow_none
             return
-        if device_mode:
+        is_tensor = torch is not None and isinstance(a, torch.Tensor)
+        if device_mode and not _is_cuda(a):
+            raise CngpError("mixing host and device arrays in one call")
+        if is_tensor:
             tdt = torch.float64 if dtype == np.float64 else torch.int32
-            if not _is_cuda(a):
-                raise CngpError("mixing host and device arrays in one call")
             if a.dtype != tdt or not a.is_contiguous():
+                if output:
+                    raise CngpError(f"output buffer must be a contiguous {tdt} tensor (got {a.dtype}, "
+                                    f"contiguous={a.is_contiguous()})")
                 a = a.to(tdt).contiguous()
             self.keep = a
             self.ptr = a.data_ptr()
         else:
-            if torch is not None and isinstance(a, torch.Tensor):
-                tdt = torch.float64 if dtype == np.float64 else torch.int32
-                if a.dtype != tdt or not a.is_contiguous():
-                    a = a.to(tdt).contiguous()
-                self.keep = a
-                self.ptr = a.data_ptr()
+            if output:
+                if not (isinstance(a, np.ndarray) and a.dtype == dtype and a.flags.c_contiguous and a.flags.writeable):
+                    raise CngpError(f"output buffer must be a writeable C-contiguous numpy array of {np.dtype(dtype)}")
             else:
                 a = np.ascontiguousarray(a, dtype=dtype)
-                self.keep = a
-                self.ptr = a.ctypes.data
+            self.keep = a
+            self.ptr = a.ctypes.data
 
 
 class GpContext:
-    def __init__(self, device: int = 0, jitter_retry: bool = False, scratch_bytes: int = 0):
+    PRECISIONS = {"f64": 0, "f32": 1}
+
+    def __init__(self, device: int = 0, jitter_retry: bool = False, scratch_bytes: int = 0, precision: str = "f64"):
+        """precision: "f64" (1e-9 parity, default) or "f32" (north_star's 1e-4 mode: the predictive mean / variance
+        phase runs as 3xTF32 on the tensor cores; arrays stay float64 at the interface)."""
         self.lib = L.load()
         cfg = L.Config()
         self.lib.cngp_default_config(C.byref(cfg))
         cfg.device = device
         cfg.jitter_retry = int(jitter_retry)
         cfg.scratch_bytes = scratch_bytes
+        cfg.precision = self.PRECISIONS[precision]
         h = C.c_void_p()
         rc = self.lib.cngp_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -100,6 +108,9 @@ class GpContext:
 
     def sync(self):
         self._check(self.lib.cngp_sync(self.h), "cngp_sync")
+
+    def set_precision(self, precision: str):
+        self._check(self.lib.cngp_set_precision(self.h, self.PRECISIONS[precision]), "cngp_set_precision")
 
     def launch_count(self) -> int:
         return int(self.lib.cngp_launch_count(self.h))
@@ -151,8 +162,9 @@ class GpContext:
         else:
             mean, var, lml, status = out
         a = [_Arg(theta, np.float64, dev), _Arg(x, np.float64, dev), _Arg(y, np.float64, dev),
-             _Arg(xstar, np.float64, dev), _Arg(mean, np.float64, dev), _Arg(var, np.float64, dev),
-             _Arg(lml, np.float64, dev, True), _Arg(status, np.int32, dev)]
+             _Arg(xstar, np.float64, dev), _Arg(mean, np.float64, dev, output=True),
+             _Arg(var, np.float64, dev, output=True), _Arg(lml, np.float64, dev, True, output=True),
+             _Arg(status, np.int32, dev, output=True)]
         self._bind_stream(dev)
         rc = self.lib.cngp_predict_batch(self.h, C.byref(k), a[0].ptr, theta_stride, a[1].ptr, a[2].ptr, a[3].ptr,
                                          xstar_stride, B, N, M, a[4].ptr, a[5].ptr, a[6].ptr, a[7].ptr,
@@ -172,7 +184,8 @@ class GpContext:
         grad = self._empty((Cn, B, P), np.float64, dev) if want_grad else None
         status = self._empty((Cn, B), np.int32, dev)
         a = [_Arg(theta, np.float64, dev), _Arg(x, np.float64, dev), _Arg(y, np.float64, dev),
-             _Arg(lml, np.float64, dev), _Arg(grad, np.float64, dev, True), _Arg(status, np.int32, dev)]
+             _Arg(lml, np.float64, dev, output=True), _Arg(grad, np.float64, dev, True, output=True),
+             _Arg(status, np.int32, dev, output=True)]
         self._bind_stream(dev)
         rc = self.lib.cngp_lml_grad_batch(self.h, C.byref(k), a[0].ptr, Cn, a[1].ptr, a[2].ptr, B, N, a[3].ptr,
                                           a[4].ptr, a[5].ptr, L.MEM_DEVICE if dev else L.MEM_HOST)
@@ -210,7 +223,7 @@ class GpContext:
         mean = np.empty((B, m_cap))
         sigma = np.empty((B, m_cap))
         m_out = C.c_int32(0)
-        status = np.empty(B, dtype=np.int32)
+        status = np.zeros(B, dtype=np.int32)
         if theta is not None:
             theta = np.ascontiguousarray(theta, dtype=np.float64)
             stride = 0 if theta.ndim == 1 else theta.shape[1]

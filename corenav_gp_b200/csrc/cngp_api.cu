@@ -16,6 +16,7 @@
 #include "gp_fit.cuh"
 #include "gp_grad.cuh"
 #include "gp_var.cuh"
+#include "gp_var32.cuh"
 
 extern "C" int cngp_launch_lookahead(const double*, const double*, long long, int, const double*, const double*,
                                      const double*, const double*, const double*, int, const cngp_stop_config*, int*,
@@ -283,6 +284,8 @@ extern "C" int cngp_create(const cngp_config* cfg, cngp_ctx** out) {
     return fail(nullptr, CNGP_ERR_CUDA, "cngp_create: no CUDA device (%s) - libcngp has no CPU fallback",
                 e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
   if (c.device < 0 || c.device >= ndev) return fail(nullptr, CNGP_ERR_INVALID, "cngp_create: bad device %d", c.device);
+  if (c.precision != CNGP_PRECISION_F64 && c.precision != CNGP_PRECISION_F32)
+    return fail(nullptr, CNGP_ERR_INVALID, "cngp_create: unknown precision mode %d", c.precision);
   CU(nullptr, cudaSetDevice(c.device));
   cudaDeviceProp prop;
   CU(nullptr, cudaGetDeviceProperties(&prop, c.device));
@@ -328,6 +331,13 @@ extern "C" int cngp_set_stream(cngp_ctx* ctx, void* s, int32_t use_own) {
   if (!ctx) return CNGP_ERR_INVALID;
   ctx->collect();
   ctx->stream = use_own ? ctx->own_stream : (cudaStream_t)s;  // s == 0 is the legacy default stream
+  return CNGP_OK;
+}
+
+extern "C" int cngp_set_precision(cngp_ctx* ctx, int32_t precision) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (precision != CNGP_PRECISION_F64 && precision != CNGP_PRECISION_F32) return fail(ctx, CNGP_ERR_INVALID, "set_precision: unknown mode %d", precision);
+  ctx->cfg.precision = precision;
   return CNGP_OK;
 }
 
@@ -407,24 +417,31 @@ struct Stage {
 // ------------------------------------------------------------------------------------------------------------
 // batched predict
 // ------------------------------------------------------------------------------------------------------------
-template <int NT_MAX, int G, int WG, int NSLOT, int CT, int KID>
+template <int NT_MAX, int G, int WG, int NSLOT, int CT, int KID, bool TAB = false>
 static int launch_var_k(cngp_ctx* ctx, VarArgs& va, long long nwin, cudaStream_t s) {
   const long long nrounds = (va.mt - va.mt0 + WG - 1) / WG;
   const long long units = nwin * nrounds;
   const long long grid = std::min<long long>((units + G - 1) / G, g_sm_count);   // persistent: one CTA per SM
   const size_t smem = var_smem_bytes(G, WG, NSLOT, CT);
-  if (KID == KID_GENERIC) {
+  if (KID == KID_GENERIC && !TAB) {
     va.kstage = (double*)ctx->buf(12, (size_t)grid * G * WG * NT_MAX * 64 * sizeof(double));
     if (!va.kstage) return CNGP_ERR_NOMEM;
   }
   const bool full = va.nt == NT_MAX && va.N == NT_MAX * 8;
-  auto kfn = full ? gp_var_kernel<NT_MAX, G, WG, NSLOT, CT, KID, true> : gp_var_kernel<NT_MAX, G, WG, NSLOT, CT, KID, false>;
+  auto kfn = full ? gp_var_kernel<NT_MAX, G, WG, NSLOT, CT, KID, true, TAB> : gp_var_kernel<NT_MAX, G, WG, NSLOT, CT, KID, false, TAB>;
   cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kfn<<<(unsigned)grid, G * WG * 32, smem, s>>>(va);
   return CNGP_OK;
 }
 template <int NT_MAX, int G, int WG, int NSLOT, int CT>
 static int launch_var(cngp_ctx* ctx, int kid, VarArgs& va, long long nwin, cudaStream_t s) {
+  if (va.n_lazy) {
+    // Stationary expression: the lag-table kernel and the lazy kernel are both launched; phase A counted the windows
+    // without a valid table (non-integer stamps) and exactly one of the two runs, the other returns at once.
+    const int rc = launch_var_k<NT_MAX, G, WG, NSLOT, CT, KID_RBF, true>(ctx, va, nwin, s);
+    if (rc) return rc;
+    ctx->launches++;
+  }
   switch (kid) {
     case KID_RBF: return launch_var_k<NT_MAX, G, WG, NSLOT, CT, KID_RBF>(ctx, va, nwin, s);
     case KID_RBF_PER: return launch_var_k<NT_MAX, G, WG, NSLOT, CT, KID_RBF_PER>(ctx, va, nwin, s);
@@ -432,6 +449,25 @@ static int launch_var(cngp_ctx* ctx, int kid, VarArgs& va, long long nwin, cudaS
     default: return launch_var_k<NT_MAX, G, WG, NSLOT, CT, KID_GENERIC>(ctx, va, nwin, s);
   }
 }
+// FP32 mode: ten warps x 16 test points per round (M = 600 -> 38 sixteen-point tiles -> 4 rounds, 95 % of the slots used)
+template <int NT_MAX>
+static int launch_var32(cngp_ctx* ctx, VarArgs& va, long long nwin, cudaStream_t s) {
+  constexpr int WG = 10, NSLOT = 3, CT = 64;
+  va.mt = (va.M + 15) / 16;
+  va.mt0 = 0;
+  const long long nrounds = (va.mt + WG - 1) / WG;
+  const long long units = nwin * nrounds;
+  const long long grid = std::min<long long>(units, g_sm_count);
+  const size_t smem = var32_smem_bytes(NSLOT, CT);
+  va.kstage = (double*)ctx->buf(12, (size_t)grid * WG * NT_MAX * 32 * 16);
+  if (!va.kstage) return CNGP_ERR_NOMEM;
+  const bool full = va.nt == NT_MAX && va.N == NT_MAX * 8;
+  auto kfn = full ? gp_var32_kernel<NT_MAX, WG, NSLOT, CT, true> : gp_var32_kernel<NT_MAX, WG, NSLOT, CT, false>;
+  cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kfn<<<(unsigned)grid, WG * 32, smem, s>>>(va);
+  return CNGP_OK;
+}
+
 template <int KID, int NW, int T>
 static void launch_fit_k(const FitArgs& fa, long long nprob, cudaStream_t s) {
   const size_t smem = fit_smem_bytes(fa.nt, NW * T);
@@ -452,6 +488,17 @@ static void launch_fit(int kid, const FitArgs& fa, long long nprob, cudaStream_t
     case KID_RBF_BROWN: launch_fit_w<KID_RBF_BROWN>(fa, nprob, s); break;
     default: launch_fit_w<KID_GENERIC>(fa, nprob, s); break;
   }
+}
+
+// every leaf a function of |x - x'| only (White: zero off the diagonal) - what the lag tables of gp_fit.cuh need
+static bool kprog_stationary(const KProg& kp) {
+  for (int u = 0; u < kp.n_leaves; ++u)
+    if (kp.leaf_type[u] == CNGP_K_BROWNIAN || kp.leaf_type[u] == CNGP_K_LINEAR) return false;
+  return true;
+}
+static bool lag_tables_enabled() {
+  const char* e = getenv("CNGP_NO_LAG_TABLES");   // tests force the lazy path with it
+  return !(e && atoi(e));
 }
 
 int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t theta_stride,
@@ -490,9 +537,16 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
 
   const int nt = (N + 7) / 8, mt = (M + 7) / 8;
   const int kid = match_fast_kernel(kp);
-  const size_t per_problem = ((size_t)tiles_in_lower(nt) * 64 + (size_t)nt * 8 * 5) * sizeof(double);
+  const bool lag_ok = kprog_stationary(kp) && lag_tables_enabled();
+  const size_t per_problem = ((size_t)tiles_in_lower(nt) * 64 + (size_t)nt * 8 * 5 +
+                              (lag_ok ? (size_t)VAR_TAB_MAX + VAR_META + (size_t)nt * 4 : 0)) * sizeof(double);
+  int* d_nlazy = nullptr;
+  if (lag_ok && !(d_nlazy = (int*)ctx->buf(16, 256))) return fail(ctx, CNGP_ERR_NOMEM, "predict: flag buffer");
   const size_t slack = 64 * 64;   // >= the largest chunk (tiles x 64 doubles)   // gp_var_kernel's first (partial) chunk may start before the first tile
-  long long chunk = std::max<long long>(1, (long long)((ctx->scratch_bytes - slack * 8) / per_problem));
+  if (ctx->scratch_bytes < slack * 8 + per_problem)
+    return fail(ctx, CNGP_ERR_NOMEM, "predict: scratch_bytes = %zu cannot hold one window (%zu bytes needed)",
+                ctx->scratch_bytes, slack * 8 + per_problem);
+  long long chunk = (long long)((ctx->scratch_bytes - slack * 8) / per_problem);
   cudaEvent_t pending_inputs = nullptr;
   auto send_inputs = [&](long long w0, cudaStream_t s) -> int {   // x, y of the slab starting at w0
     if (w0 >= B) return 0;
@@ -521,10 +575,22 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
     double* Lbuf = ctx->scratch + slack;
     double* zbuf = Lbuf + (size_t)nw * tiles_in_lower(nt) * 64;
     double* fbuf = zbuf + (size_t)nw * nt * 8;
+    double* tbuf = fbuf + (size_t)nw * nt * 8 * 4;                 // lag tables | meta | integer stamps
+    double* mbuf = tbuf + (size_t)nw * VAR_TAB_MAX;
+    int* xibuf = (int*)(mbuf + (size_t)nw * VAR_META);
     FitArgs fa;
+    memset(&fa, 0, sizeof fa);
     fa.kp = kp;
     fa.theta = d_theta; fa.theta_stride = theta_stride; fa.theta_mode = theta_stride ? 1 : 0;
     fa.win_map = nullptr;
+    if (lag_ok) {
+      fa.lag_ok = 1;
+      fa.xstar = d_xs; fa.xstar_stride = xstar_stride; fa.M = M;
+      fa.ktab = M > 0 ? tbuf : nullptr; fa.kmeta = M > 0 ? mbuf : nullptr; fa.kxi = xibuf; fa.n_lazy = d_nlazy;
+      CU(ctx, cudaMemsetAsync(d_nlazy, 0, sizeof(int), ctx->stream));
+    }
+    const bool f32 = ctx->cfg.precision == CNGP_PRECISION_F32;
+    fa.f32_factor = (f32 && M > 0) ? 1 : 0;
     fa.x = d_x; fa.y = d_y; fa.N = N; fa.nt = nt; fa.n_windows = (int)B; fa.problem0 = w0;
     fa.L = Lbuf; fa.z = zbuf; fa.feat = fbuf; fa.lml = d_lml; fa.logdet = nullptr; fa.quad = nullptr;
     fa.status = d_status;
@@ -535,7 +601,9 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
     ctx->end();
     if (M > 0) {
       VarArgs va;
+      memset(&va, 0, sizeof va);
       va.kp = kp;
+      va.ktab = tbuf; va.kmeta = mbuf; va.kxi = xibuf; va.n_lazy = lag_ok ? d_nlazy : nullptr;
       va.theta = d_theta; va.theta_stride = theta_stride; va.theta_mode = theta_stride ? 1 : 0;
       va.xstar = d_xs; va.xstar_stride = xstar_stride;
       va.N = N; va.nt = nt; va.M = M; va.mt = mt; va.mt0 = 0; va.window0 = w0; va.n_windows_launch = nw;
@@ -544,7 +612,14 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
       va.kstage = nullptr;
       ctx->begin(CNGP_PROF_VAR);
       int vrc;
-      if (nt <= 8) vrc = launch_var<8, 1, 16, 6, 16>(ctx, kid, va, nw, ctx->stream);
+      if (f32) {
+        va.n_lazy = nullptr;
+        va.kmeta = lag_ok ? mbuf : nullptr;      // the FP32 kernel picks table or interpreter per window
+        if (nt <= 8) vrc = launch_var32<8>(ctx, va, nw, ctx->stream);
+        else if (nt <= 16) vrc = launch_var32<16>(ctx, va, nw, ctx->stream);
+        else vrc = launch_var32<32>(ctx, va, nw, ctx->stream);
+      }
+      else if (nt <= 8) vrc = launch_var<8, 1, 16, 6, 16>(ctx, kid, va, nw, ctx->stream);
       else if (nt <= 16) vrc = launch_var<16, 1, 16, 6, 16>(ctx, kid, va, nw, ctx->stream);
 #ifdef CNGP_VAR_TUNE   // tuning builds only: alternative shapes selected by the environment
       else if (getenv("CNGP_VAR_VARIANT") && atoi(getenv("CNGP_VAR_VARIANT")) == 1) vrc = launch_var<32, 1, 12, 4, 32>(ctx, kid, va, nw, ctx->stream);
@@ -632,7 +707,10 @@ int cngp_lml_grad_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* t
   const int nt = (N + 7) / 8;
   const size_t ltiles = (size_t)tiles_in_lower(nt) * 64;
   const size_t per_problem = (ltiles * (grad ? 2 : 1) + (size_t)nt * 8 * 2) * sizeof(double);
-  const long long chunk = std::max<long long>(1, (long long)(ctx->scratch_bytes / per_problem));
+  if (ctx->scratch_bytes < per_problem)
+    return fail(ctx, CNGP_ERR_NOMEM, "lml_grad: scratch_bytes = %zu cannot hold one problem (%zu bytes needed)",
+                ctx->scratch_bytes, per_problem);
+  const long long chunk = (long long)(ctx->scratch_bytes / per_problem);
   for (long long p0 = 0; p0 < n_prob; p0 += chunk) {
     const long long np = std::min<long long>(chunk, n_prob - p0);
     double* Lbuf = ctx->scratch;
@@ -640,7 +718,9 @@ int cngp_lml_grad_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* t
     double* zbuf = grad ? Wbuf + (size_t)np * ltiles : Wbuf;
     double* abuf = zbuf + (size_t)np * nt * 8;
     FitArgs fa;
+    memset(&fa, 0, sizeof fa);
     fa.kp = kp;
+    fa.lag_ok = (kprog_stationary(kp) && lag_tables_enabled()) ? 1 : 0;   // K(X,X) by integer lag when the stamps allow
     fa.theta = d_theta; fa.theta_stride = P; fa.theta_mode = d_map ? 3 : 2;
     fa.win_map = d_map;
     fa.x = d_x; fa.y = d_y; fa.N = N; fa.nt = nt; fa.n_windows = (int)B; fa.problem0 = p0;

@@ -45,6 +45,20 @@ __device__ __forceinline__ void tile_store(double* tile, int lane, const tile2& 
   *reinterpret_cast<double2*>(tile + 2 * lane) = make_double2(t.a, t.b);
 }
 
+// FP32 mode (gp_var32.cuh): a factor tile is stored SPLIT for the 3xTF32 tensor-core product - lane 4r+q writes
+// float4 {hi(T[r][2q]), hi(T[r][2q+1]), lo(T[r][2q]), lo(T[r][2q+1])}, hi = tf32(x), lo = tf32(x - hi): 512 B as before.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void tile_store_split(double* tile, int lane, const tile2& t) {
+  const float a = (float)t.a, b = (float)t.b;
+  const uint32_t ha = to_tf32(a), hb = to_tf32(b);
+  const uint32_t la = to_tf32(a - __uint_as_float(ha)), lb = to_tf32(b - __uint_as_float(hb));
+  *reinterpret_cast<uint4*>(reinterpret_cast<char*>(tile) + 16 * lane) = make_uint4(ha, hb, la, lb);
+}
+
 // Packed lower-triangular tile storage, column-major: column j holds tiles i = j..nt-1 and starts after the
 // nt + (nt-1) + ... tiles of columns 0..j-1.  Seen from the END of the buffer, column j (J = nt-1-j) starts
 // (J+1)(J+2)/2 tiles before the end - independent of nt - and the forward substitution of gp_var.cuh consumes the
@@ -53,6 +67,18 @@ __host__ __device__ __forceinline__ int tile_index(int i, int j, int nt) {
   return j * nt - j * (j - 1) / 2 + (i - j);
 }
 __host__ __device__ __forceinline__ int tiles_in_lower(int nt) { return nt * (nt + 1) / 2; }
+
+// Lag tables.  The reference's stamps are integer update counts (CoreNav.cpp:286) and its prediction grid has step 1
+// (gp_slip_node.py:45), so for a stationary expression k(x, x') is a function of the INTEGER lag |x - x'| only: at most
+// span + horizon + 1 distinct values per window instead of N(N+1)/2 + N M evaluations.  gp_fit_kernel detects this per
+// window (every stamp and every test point an integer below 2^26, which also makes GPy's expanded-form r^2 exact), builds
+// the table once - with the same interpreter as the lazy path - keeps the lags of K(X,X) in shared memory for its own
+// assembly and writes the whole table out for gp_var_kernel.  Non-integer stamps or other kernels take the lazy
+// evaluators as before.
+constexpr int FIT_TAB_MAX = 1024;     // lags of K(X,X) kept in shared memory (span of the training stamps)
+constexpr int VAR_TAB_MAX = 2048;     // lags of the whole table (training + test stamps), doubles per window in scratch
+constexpr int VAR_META = 8;           // doubles per window: [0] Kdiag(x*) (constant for stationary kernels), [1] base stamp,
+                                      // [2] noise variance, [3] 1.0 if the table is valid
 
 // ---- mbarrier + bulk asynchronous copy (TMA, 1-D) helpers ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -71,6 +71,16 @@ struct FitArgs {
   double* quad;          // [n_problems] or null   y' Ky^-1 y
   int* status;           // [n_problems] or null
   int jitter_retry;
+  // lag tables (see above).  lag_ok: the expression is stationary (host check); the rest may be null (fit-only callers)
+  int lag_ok;
+  const double* xstar;   // [n_windows][M] or [M]: test stamps, so that the table covers the cross-covariance lags
+  long long xstar_stride;
+  int M;
+  double* ktab;          // [chunk][VAR_TAB_MAX]
+  double* kmeta;         // [chunk][VAR_META]
+  int* kxi;              // [chunk][nt*8]  training stamps as integer offsets from the base stamp
+  int f32_factor;        // FP32 mode: write the factor tiles split hi/lo TF32 (tile_store_split) for gp_var32_kernel
+  int* n_lazy;           // += 1 for every window of the launch whose table is NOT valid (gp_var_kernel picks its path on it)
   // KID_TILES only (large-N blocked Cholesky, chol_large.cu): the SPD block is read from tile storage instead of being
   // evaluated - tile (i, j) of the block at Asrc + j * a_col_stride + i * 64 (lower tiles only are read).
   const double* Asrc;
@@ -132,6 +142,16 @@ __device__ __forceinline__ int chol8_inv8(tile2 c, int lane, double* linv, doubl
 
 template <int N> struct FitIC { static constexpr int value = N; };
 
+// Row residue of worker warp w (its rows are residue + NW t).  Identity.  Rows with a higher index live longer, so
+// residue r carries pass work ~ sum_t (r + NW t)^2 and the sub-partitions (warp id % 4) are unevenly loaded; dealing the
+// residues so that the four sub-partitions carry equal work was measured (tools/fit_bench.cu, round 2): {8,4,0} {7,5,1}
+// {6,3,2} {9,10}+diag 2.23 ms, {9,0,10} {8,1,2} {7,3,4} {5,6}+diag 2.29 ms, identity 2.19 ms - the per-column critical
+// path is the diagonal warp's chol8 + the panel phase, not the heaviest worker, so balancing the passes buys nothing.
+template <int NW>
+__device__ __forceinline__ int fit_residue(int w) {
+  return w;
+}
+
 // NW workers, T row-tile slots per worker: nt <= NW * T.
 template <int KID, int NW, int T>
 __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_kernel(const FitArgs a) {
@@ -148,8 +168,15 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
   __shared__ double dpiv[NPAD];          // diagonal of L (pivots), logged in parallel at the end
   __shared__ double s_red[NW + 1], s_red2[NW + 1];
   __shared__ int s_fail;
+  __shared__ double s_tab[KID == KID_TILES ? 1 : FIT_TAB_MAX];   // k by integer lag, lags 0 .. span
+  __shared__ int s_xi[KID == KID_TILES ? 2 : NPAD];              // training stamps minus the base stamp
+  __shared__ double s_mm[4][NW + 1];
+  __shared__ int s_okv[NW + 1];
+  __shared__ int s_tabmode;
+  __shared__ double s_kdiag;
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int wr = fit_residue<NW>(w);               // row residue of a worker warp
   const int r = lane >> 2, q = lane & 3;
   const long long lp = blockIdx.x;                 // problem within this launch
   const long long p = a.problem0 + lp;             // global problem
@@ -180,11 +207,78 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
       fp[i] = f.x; fp[nt * 8 + i] = f.xx; fp[2 * nt * 8 + i] = f.c; fp[3 * nt * 8 + i] = f.s;
     }
   }
-  if (KID == KID_GENERIC) {
+  if (KID == KID_GENERIC || (KID != KID_TILES && a.lag_ok)) {
     if (tid < a.kp.n_leaves) hc[tid] = leaf_prepare(a.kp.leaf_type[tid], th + a.kp.leaf_param[tid]);
     if (tid == 0) kps = a.kp;
   }
+  if (tid == 0) s_tabmode = 0;
   __syncthreads();
+
+  // ---- lag table (stationary expression, integer stamps) ----
+  if (KID != KID_TILES && a.lag_ok) {
+    const double big = 67108864.0;   // 2^26: x^2 and x x' stay exact integers, r^2 of the expanded form is exact
+    double xlo = 1e300, xhi = -1e300, slo = 1e300, shi = -1e300;
+    int ok = 1;
+    for (int i = tid; i < N; i += FIT_THREADS) {
+      const double v = fx[i];
+      ok &= (v == rint(v)) && (fabs(v) < big);
+      xlo = fmin(xlo, v); xhi = fmax(xhi, v);
+    }
+    if (a.xstar) {
+      const double* xs = a.xstar + (a.xstar_stride ? (long long)win * a.xstar_stride : 0);
+      for (int i = tid; i < a.M; i += FIT_THREADS) {
+        const double v = xs[i];
+        ok &= (v == rint(v)) && (fabs(v) < big);
+        slo = fmin(slo, v); shi = fmax(shi, v);
+      }
+    }
+    for (int o = 16; o; o >>= 1) {
+      xlo = fmin(xlo, __shfl_xor_sync(0xffffffffu, xlo, o)); xhi = fmax(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+      slo = fmin(slo, __shfl_xor_sync(0xffffffffu, slo, o)); shi = fmax(shi, __shfl_xor_sync(0xffffffffu, shi, o));
+      ok &= __shfl_xor_sync(0xffffffffu, ok, o);
+    }
+    if (lane == 0) { s_mm[0][w] = xlo; s_mm[1][w] = xhi; s_mm[2][w] = slo; s_mm[3][w] = shi; s_okv[w] = ok; }
+    __syncthreads();
+    for (int i = 0; i <= NW; ++i) {
+      xlo = fmin(xlo, s_mm[0][i]); xhi = fmax(xhi, s_mm[1][i]); slo = fmin(slo, s_mm[2][i]); shi = fmax(shi, s_mm[3][i]);
+      ok &= s_okv[i];
+    }
+    const double base = fmin(xlo, slo);
+    const double span = xhi - xlo;                                   // largest lag inside K(X,X)
+    const double dmax = fmax(xhi, shi) - base;                       // largest lag of K(X,X) and K(X,X*)
+    const bool fit_tab = ok && span < (double)FIT_TAB_MAX;
+    const bool var_tab = ok && a.ktab && dmax < (double)VAR_TAB_MAX;
+    if (fit_tab || var_tab) {
+      const int nl = (int)(var_tab ? dmax : span) + 1;
+      double* gt = var_tab ? a.ktab + lp * (long long)VAR_TAB_MAX : nullptr;
+      for (int d = tid; d < nl; d += FIT_THREADS) {
+        const double v = keval_generic_cross(&kps, hc, (double)d, 0.0);
+        if (fit_tab && d < FIT_TAB_MAX && (double)d <= span) s_tab[d] = v;
+        if (gt) gt[d] = v;
+      }
+      for (int i = tid; i < nt * 8; i += FIT_THREADS) {
+        const int xi = i < N ? (int)(fx[i] - base) : 0;
+        s_xi[i] = xi;
+        if (var_tab) a.kxi[lp * (long long)(nt * 8) + i] = xi;
+      }
+      if (tid == 0) {
+        s_tabmode = fit_tab ? 1 : 0;
+        s_kdiag = keval_generic_sym(&kps, hc, 0.0, 0.0, true);     // K(X,X) diagonal (White included)
+      }
+    }
+    if (tid == 0 && a.kmeta) {
+      double* km = a.kmeta + lp * (long long)VAR_META;
+      km[0] = kdiag_eval(kps, hc, 0.0);
+      km[1] = base;
+      km[2] = noise;
+      km[3] = var_tab ? 1.0 : 0.0;
+      if (!var_tab && a.n_lazy) atomicAdd(a.n_lazy, 1);
+    }
+    __syncthreads();
+  } else if (KID != KID_TILES && tid == 0 && a.n_lazy) {
+    atomicAdd(a.n_lazy, 1);
+  }
+  const bool tabmode = KID != KID_TILES && s_tabmode != 0;
 
   const bool full_window = N == 8 * nt;
   auto feat_at = [&](int i) -> PointFeat {
@@ -201,6 +295,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
     }
     return (row == col) ? 1.0 : 0.0;
   };
+  // lag-table form of a Ky tile: xr = integer stamp of my row, xc = stamps of my two columns
+  auto ky_tab = [&](int xr, int2 xc, int i, int c, double dadd) -> tile2 {
+    const int c0 = 8 * c + 2 * q, c1 = c0 + 1, row = 8 * i + r;
+    double v0 = s_tab[abs(xr - xc.x)], v1 = s_tab[abs(xr - xc.y)];     // two shared-memory lookups by integer lag
+    if (i == c) {    // true diagonal entries: K(x,x) of the expression (White included) + noise + jitter
+      if (row == c0) v0 = s_kdiag + dadd;
+      if (row == c1) v1 = s_kdiag + dadd;
+    }
+    if (!full_window) {   // identity padding beyond N
+      if (row >= N || c0 >= N) v0 = (row == c0) ? 1.0 : 0.0;
+      if (row >= N || c1 >= N) v1 = (row == c1) ? 1.0 : 0.0;
+    }
+    return tile2{v0, v1};
+  };
   // tile (i, c) of Ky in the lane layout (dadd on the diagonal entries), evaluated or - KID_TILES - loaded
   auto ky_tile = [&](int i, int c, double dadd) -> tile2 {
     if (KID == KID_TILES) {
@@ -208,6 +316,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
       return tile2{av.x, av.y};
     }
     const int c0 = 8 * c + 2 * q, c1 = c0 + 1, row = 8 * i + r;
+    if (tabmode) return ky_tab(s_xi[row], *reinterpret_cast<const int2*>(s_xi + c0), i, c, dadd);
     if (KID != KID_GENERIC && full_window && i != c) {   // interior tile of an unpadded window: no diagonal, no padding
       const PointFeat fr = feat_at(row);
       const double2 x2 = *reinterpret_cast<const double2*>(fx + c0), xx2 = *reinterpret_cast<const double2*>(fxx + c0);
@@ -240,7 +349,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
       double s = 0.0;
       for (int i = tid; i < N; i += FIT_THREADS) {
         const PointFeat f = feat_at(i);
-        s += ky_entry(i, i, f, f) + noise + CNGP_JITTER;
+        s += (tabmode ? s_kdiag : ky_entry(i, i, f, f)) + noise + CNGP_JITTER;
       }
       for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) s_red[w] = s;
@@ -267,7 +376,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
         if (lane == 0 && f && s_fail == 0) s_fail = 8 * j + f;
         FIT_STAMP(0);
         named_bar_arrive(1, FIT_THREADS);                           // inv(L_jj) is in linv
-        tile_store(Lp + (long long)tile_index(j, j, nt) * 64, lane, tile_load(linv, lane));
+        if (a.f32_factor) tile_store_split(Lp + (long long)tile_index(j, j, nt) * 64, lane, tile_load(linv, lane));
+        else tile_store(Lp + (long long)tile_index(j, j, nt) * 64, lane, tile_load(linv, lane));
         named_bar_sync(2, FIT_THREADS);                             // column j stored, dpart of column j+1 parked
         FIT_STAMP(1);
         if (j + 1 < nt) {
@@ -280,11 +390,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
       }
     } else {
       // ================= worker warps =================
-      // slot t of this warp is row tile i = w + NW t, for every column
+      // slot t of this warp is row tile i = wr + NW t, for every column (wr: the warp's row residue, see fit_residue)
       tile2 Ccur[T], Lt[T];
+      int xrow[T];                  // lag-table mode: integer stamp of my row in slot t
+#pragma unroll
+      for (int t = 0; t < T; ++t) xrow[t] = (tabmode && wr + NW * t < nt) ? s_xi[8 * (wr + NW * t) + r] : 0;
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        const int i = w + NW * t;
+        const int i = wr + NW * t;
         Ccur[t] = (i >= 1 && i < nt) ? ky_tile(i, 0, dadd) : tile2{0.0, 0.0};   // (0,0) is the diagonal warp's
         Lt[t] = tile2{0.0, 0.0};
       }
@@ -293,8 +406,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
       for (int j = 0; j < nt; ++j) {
         const int c = j + 1;
         // ---- (b) look-ahead: partial sums of column c over k < j, Ky tiles of column c ----
-        const int t0 = c > w ? (c - w + NW - 1) / NW : 0;     // first slot with a row >= c
-        const bool own_diag = t0 < T && w + NW * t0 == c && c < nt;
+        const int t0 = c > wr ? (c - wr + NW - 1) / NW : 0;     // first slot with a row >= c
+        const bool own_diag = t0 < T && wr + NW * t0 == c && c < nt;
         tile2 S0[T], S1[T], Kn[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) {
@@ -302,13 +415,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
           S1[t] = tile2{0.0, 0.0};
           Kn[t] = tile2{0.0, 0.0};
         }
-        if (c < nt && w + NW * t0 < nt && t0 < T) {
+        if (c < nt && wr + NW * t0 < nt && t0 < T) {
           // pool pass over slots T0..T-1 (compile-time T0): Y = (c,k) and X_t = (i_t,k) sit in the same pool column.
           // Slots whose row is beyond nt-1 read (and never use) whatever follows the column - see fit_smem_bytes.
           auto pass = [&](auto t0c, int k0, int k1, const double* pY) {
             constexpr int T0 = decltype(t0c)::value;
             if (k0 >= k1) return;
-            const double* pX = pY + (w - c) * 64;
+            const double* pX = pY + (wr - c) * 64;
             int pitch = (nt - 1) * 64;
             const double* zp = zs + 8 * k0 + 2 * q;
             tile2 Y = tile_load(pY, 0), X[T], Yn{0.0, 0.0}, Xn[T];
@@ -357,12 +470,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
           else both(FitIC<(T > 3 ? 3 : 0)>{});
           FIT_STAMP(0);
           // Ky tiles of column c (never stored); the diagonal row's partial result goes to the diagonal warp
+          int2 xc2 = make_int2(0, 0);
+          if (tabmode) xc2 = *reinterpret_cast<const int2*>(s_xi + 8 * c + 2 * q);
 #pragma unroll
           for (int t = 0; t < T; ++t) {
-            const int i = w + NW * t;
+            const int i = wr + NW * t;
             if (t >= t0 && i < nt) {
               S0[t].a += S1[t].a; S0[t].b += S1[t].b;
-              Kn[t] = ky_tile(i, c, dadd);
+              Kn[t] = tabmode ? ky_tab(xrow[t], xc2, i, c, dadd) : ky_tile(i, c, dadd);
               if (i == c) tile_store(dpart[c & 1], lane, tile2{Kn[t].a - S0[t].a, Kn[t].b - S0[t].b});
             }
           }
@@ -377,16 +492,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
           double* pcol = pool + pool_idx(j, j) * 64;
 #pragma unroll
           for (int t = 0; t < T; ++t) {
-            const int i = w + NW * t;
+            const int i = wr + NW * t;
             if (i > j && i < nt) {
               tile2 L{0.0, 0.0};
               tile_mma(L, Ccur[t], Yinv);
               Lt[t] = L;
               tile_store(pcol + (i - j) * 64, lane, L);
-              tile_store(colj + (i - j) * 64, lane, L);
+              if (a.f32_factor) tile_store_split(colj + (i - j) * 64, lane, L);
+              else tile_store(colj + (i - j) * 64, lane, L);
             }
           }
-          if (w == j % NW) {
+          if (wr == j % NW) {
             // z_j = inv(L_jj) (y_j - sum_k L(j,k) z_k): reduce the lane partials over q, then an 8x8 mat-vec in-warp
             double s = za + zb;
             s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -408,7 +524,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
           const tile2 Y = tile_load(pool + pool_idx(c, j) * 64, lane);
 #pragma unroll
           for (int t = 0; t < T; ++t) {
-            const int i = w + NW * t;
+            const int i = wr + NW * t;
             if (i > c && i < nt) {
               tile_mma(S0[t], Lt[t], Y);
               Ccur[t] = tile2{Kn[t].a - S0[t].a, Kn[t].b - S0[t].b};

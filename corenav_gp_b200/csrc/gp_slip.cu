@@ -27,11 +27,8 @@ using namespace cngp_host;
 
 namespace {
 
-struct DevMem {
-  void* p = nullptr;
-  ~DevMem() { if (p) cudaFree(p); }
-  bool alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)) == cudaSuccess; }
-};
+// grow-only device buffers of the context (slots 30..36 belong to the optimiser): no cudaMalloc / cudaFree per call
+enum { SLOT_OPT_X = 30, SLOT_OPT_Y, SLOT_OPT_TH, SLOT_OPT_MAP, SLOT_OPT_LML, SLOT_OPT_GRAD, SLOT_OPT_ST };
 
 }  // namespace
 
@@ -51,13 +48,23 @@ extern "C" int cngp_optimize_batch(cngp_ctx* ctx, const cngp_kernel* kernel, con
   for (int64_t b = 0; b < B; ++b)
     opt[b].init(theta0 ? theta0 + (theta0_stride ? b * theta0_stride : 0) : ones.data(), P, max_iters);
 
-  DevMem dx, dy, dth, dmap, dlml, dgrad, dst;
+  // Everything below is ordered on the context's stream on the context's device: the uploads are cudaMemcpyAsync on
+  // that stream (the kernels run there, and it is a non-blocking stream, so legacy-stream copies would not order them).
+  if (cudaSetDevice(cngp_ctx_device(ctx)) != cudaSuccess) return cngp_set_error(ctx, CNGP_ERR_CUDA, "optimize: cudaSetDevice failed");
+  cudaStream_t s = cngp_ctx_stream(ctx);
+  struct { void* p; } dx, dy, dth, dmap, dlml, dgrad, dst;
   const size_t xy = sizeof(double) * (size_t)B * N;
-  if (!dx.alloc(xy) || !dy.alloc(xy) || !dth.alloc(sizeof(double) * B * P) || !dmap.alloc(sizeof(int) * B) ||
-      !dlml.alloc(sizeof(double) * B) || !dgrad.alloc(sizeof(double) * B * P) || !dst.alloc(sizeof(int) * B))
+  dx.p = cngp_ctx_buf(ctx, SLOT_OPT_X, xy);
+  dy.p = cngp_ctx_buf(ctx, SLOT_OPT_Y, xy);
+  dth.p = cngp_ctx_buf(ctx, SLOT_OPT_TH, sizeof(double) * B * P);
+  dmap.p = cngp_ctx_buf(ctx, SLOT_OPT_MAP, sizeof(int) * B);
+  dlml.p = cngp_ctx_buf(ctx, SLOT_OPT_LML, sizeof(double) * B);
+  dgrad.p = cngp_ctx_buf(ctx, SLOT_OPT_GRAD, sizeof(double) * B * P);
+  dst.p = cngp_ctx_buf(ctx, SLOT_OPT_ST, sizeof(int) * B);
+  if (!dx.p || !dy.p || !dth.p || !dmap.p || !dlml.p || !dgrad.p || !dst.p)
     return cngp_set_error(ctx, CNGP_ERR_NOMEM, "optimize: device allocation failed");
-  if (cudaMemcpy(dx.p, x, xy, cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(dy.p, y, xy, cudaMemcpyHostToDevice) != cudaSuccess)
+  if (cudaMemcpyAsync(dx.p, x, xy, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+      cudaMemcpyAsync(dy.p, y, xy, cudaMemcpyHostToDevice, s) != cudaSuccess)
     return cngp_set_error(ctx, CNGP_ERR_CUDA, "optimize: upload failed");
 
   std::vector<int> active;
@@ -71,17 +78,17 @@ extern "C" int cngp_optimize_batch(cngp_ctx* ctx, const cngp_kernel* kernel, con
     const size_t na = active.size();
     for (size_t a = 0; a < na; ++a)
       for (int i = 0; i < P; ++i) th[a * P + i] = softplus(opt[active[a]].zt[i]);
-    if (cudaMemcpy(dth.p, th.data(), sizeof(double) * na * P, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(dmap.p, active.data(), sizeof(int) * na, cudaMemcpyHostToDevice) != cudaSuccess)
+    if (cudaMemcpyAsync(dth.p, th.data(), sizeof(double) * na * P, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(dmap.p, active.data(), sizeof(int) * na, cudaMemcpyHostToDevice, s) != cudaSuccess)
       return cngp_set_error(ctx, CNGP_ERR_CUDA, "optimize: upload failed");
     int rc = cngp_lml_grad_impl(ctx, &kk, (const double*)dth.p, (int64_t)na, (const double*)dx.p, (const double*)dy.p, B, N,
                                 (double*)dlml.p, (double*)dgrad.p, (int*)dst.p, CNGP_MEM_DEVICE, (const int*)dmap.p);
     if (rc) return rc;
-    if ((rc = cngp_sync(ctx))) return rc;
-    if (cudaMemcpy(lml.data(), dlml.p, sizeof(double) * na, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(grad.data(), dgrad.p, sizeof(double) * na * P, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(status.data(), dst.p, sizeof(int) * na, cudaMemcpyDeviceToHost) != cudaSuccess)
+    if (cudaMemcpyAsync(lml.data(), dlml.p, sizeof(double) * na, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(grad.data(), dgrad.p, sizeof(double) * na * P, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(status.data(), dst.p, sizeof(int) * na, cudaMemcpyDeviceToHost, s) != cudaSuccess)
       return cngp_set_error(ctx, CNGP_ERR_CUDA, "optimize: download failed");
+    if ((rc = cngp_sync(ctx))) return rc;     // the host state machines need the values; th / active are re-written next
     for (size_t a = 0; a < na; ++a) {
       Optimizer& o = opt[active[a]];
       double fv;
@@ -112,6 +119,7 @@ extern "C" int cngp_gp_slip_batch(cngp_ctx* ctx, const cngp_kernel* kernel, cons
     return cngp_set_error(ctx, CNGP_ERR_INVALID, "gp_slip: bad argument");
   *m_out = 0;
   if (B == 0) return CNGP_OK;
+  if (cudaSetDevice(cngp_ctx_device(ctx)) != cudaSuccess) return cngp_set_error(ctx, CNGP_ERR_CUDA, "gp_slip: cudaSetDevice failed");
   cngp_kernel kk = *kernel;
   if (cngp_kernel_finalize(&kk) != CNGP_OK) return cngp_set_error(ctx, CNGP_ERR_INVALID, "gp_slip: invalid kernel expression");
   const int P = kk.n_params + 1;

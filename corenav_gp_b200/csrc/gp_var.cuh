@@ -54,6 +54,12 @@ struct VarArgs {
   double* var;             // [n_windows][M]
   int sigma_mode;          // 0: var;  1: write sigma = 2 sqrt(var) instead (gp_slip_node.py:61)
   double* kstage;          // generic kernels only: [grid][warps][nt_max*64] staging of K*^T tiles
+  // lag-table path (gp_fit.cuh "Lag tables"): K*(i,k) = ktab[|x*_k - x_i|], phase A output
+  const double* ktab;      // [chunk][VAR_TAB_MAX]
+  const double* kmeta;     // [chunk][VAR_META]
+  const int* kxi;          // [chunk][nt*8]
+  const int* n_lazy;       // windows of this launch without a valid table: the TAB kernel runs iff it is 0, the lazy one
+                           // iff it is not (both are launched; one of them returns at once).  null: lazy only.
 };
 
 struct VarGroupShared {
@@ -81,8 +87,11 @@ static __device__ __noinline__ void var_issue_chunk(const VarGroupShared* sh, in
 }
 
 // FULL: nt == NT_MAX and N == 8 nt (no padding) - drops every per-column guard from the unrolled code.
-template <int NT_MAX, int G, int WG, int NSLOT, int VAR_CT, int KID, bool FULL>
+// TAB: K* comes from the window's lag table (two cached global loads per tile and lane) instead of being evaluated -
+// nothing but the DMMA stream and the mean / variance reductions is left on the FP64 pipe.  KID is ignored then.
+template <int NT_MAX, int G, int WG, int NSLOT, int VAR_CT, int KID, bool FULL, bool TAB = false>
 __global__ void __launch_bounds__(G * WG * 32, 1) gp_var_kernel(const VarArgs a) {
+  if (a.n_lazy && ((*a.n_lazy == 0) != TAB)) return;
   static_assert(NSLOT <= VAR_MAX_SLOTS && VAR_CT <= VAR_MAX_CT, "ring too deep / chunk too large");
   constexpr int WARPS = G * WG;
   constexpr int VAR_CHUNK_DOUBLES = VAR_CT * 64;
@@ -109,7 +118,7 @@ __global__ void __launch_bounds__(G * WG * 32, 1) gp_var_kernel(const VarArgs a)
   const uint32_t ring_u32 = smem_u32(ring);
   const uint32_t full_u32 = smem_u32(&sh.full[0]);
 
-  if (threadIdx.x == 0 && KID == KID_GENERIC) kps = a.kp;
+  if (threadIdx.x == 0 && KID == KID_GENERIC && !TAB) kps = a.kp;
   const uint32_t empty_u32 = smem_u32(&sh.empty[0]);
   if (wg == 0 && lane == 0) {
     for (int s = 0; s < NSLOT; ++s) { mbar_init(full_u32 + 8 * s, 1); mbar_init(empty_u32 + 8 * s, WG); }
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(G * WG * 32, 1) gp_var_kernel(const VarArgs a)
   __syncthreads();
 
   LeafConst* hc = hc_all[KID == KID_GENERIC ? w : 0];
-  double* kst = (KID == KID_GENERIC) ? a.kstage + ((size_t)blockIdx.x * WARPS + w) * (size_t)(NT_MAX * 64) + 2 * lane : nullptr;
+  double* kst = (KID == KID_GENERIC && !TAB) ? a.kstage + ((size_t)blockIdx.x * WARPS + w) * (size_t)(NT_MAX * 64) + 2 * lane : nullptr;
   int g = 0;   // chunk counter of this warp within its group's stream (over units x chunks)
 
   for (long long u = unit0; u < n_units; u += unit_stride) {
@@ -162,7 +171,8 @@ __global__ void __launch_bounds__(G * WG * 32, 1) gp_var_kernel(const VarArgs a)
     }
 
     FastK<KID> fk;
-    if (KID == KID_GENERIC) {
+    if (TAB) {
+    } else if (KID == KID_GENERIC) {
       __syncwarp();
       if (lane < a.kp.n_leaves) hc[lane] = leaf_prepare(a.kp.leaf_type[lane], th + a.kp.leaf_param[lane]);
       __syncwarp();
@@ -177,16 +187,32 @@ __global__ void __launch_bounds__(G * WG * 32, 1) gp_var_kernel(const VarArgs a)
     }
     const double* fp = a.feat + lw * (long long)(4 * n8) + 2 * q;
     const double* zp = a.z + lw * (long long)n8 + 2 * q;
-    const double noise = th[a.kp.n_params];
+    const double* km = TAB ? a.kmeta + lw * (long long)VAR_META : nullptr;
+    const double noise = TAB ? km[2] : th[a.kp.n_params];
     const bool bad = a.status && a.status[win] < 0;
 
     const int m = min(8 * m8 + r, M - 1);
     const double xm = a.xstar[(a.xstar_stride ? win * a.xstar_stride : 0) + m];
     PointFeat fm{xm, 0.0, 0.0, 0.0};
-    if (KID != KID_GENERIC) fm = fk.point(xm);
+    if (!TAB && KID != KID_GENERIC) fm = fk.point(xm);
+    const double* ktab = TAB ? a.ktab + lw * (long long)VAR_TAB_MAX : nullptr;
+    const int* xip = TAB ? a.kxi + lw * (long long)n8 + 2 * q : nullptr;
+    const int mi = TAB ? (int)(xm - km[1]) : 0;        // my test stamp as an offset from the window's base stamp
 
     // K*^T tile of training tile column j = nt-1-J (rows: my 8 test points), in the lane layout
     auto kstar_tile = [&](const int J) -> double2 {
+      if (TAB) {
+        const int c0 = 8 * (nt - 1 - J);
+        const int2 xi2 = __ldg(reinterpret_cast<const int2*>(xip + c0));
+        double2 v;
+        v.x = __ldg(ktab + abs(mi - xi2.x));
+        v.y = __ldg(ktab + abs(mi - xi2.y));
+        if (!FULL) {
+          if (c0 + 2 * q >= N) v.x = 0.0;
+          if (c0 + 2 * q + 1 >= N) v.y = 0.0;
+        }
+        return v;
+      }
       if (KID == KID_GENERIC) return *reinterpret_cast<const double2*>(kst + J * 64);
       const int c0 = 8 * (nt - 1 - J);     // + 2q is folded into fp
       const double2 x2 = *reinterpret_cast<const double2*>(fp + c0);
@@ -205,7 +231,7 @@ __global__ void __launch_bounds__(G * WG * 32, 1) gp_var_kernel(const VarArgs a)
       }
       return v;
     };
-    if (KID == KID_GENERIC) {   // rolled up-front evaluation through the interpreter (no accumulators live yet)
+    if (!TAB && KID == KID_GENERIC) {   // rolled up-front evaluation through the interpreter (no accumulators live yet)
 #pragma unroll 1
       for (int J = nt - 1; J >= 0; --J) {
         const int c0 = 8 * (nt - 1 - J) + 2 * q;
@@ -273,7 +299,7 @@ __global__ void __launch_bounds__(G * WG * 32, 1) gp_var_kernel(const VarArgs a)
     ms += __shfl_xor_sync(0xffffffffu, ms, 1);
     ms += __shfl_xor_sync(0xffffffffu, ms, 2);
     if (q == 0 && 8 * m8 + r < M) {
-      const double kss = (KID == KID_GENERIC) ? kdiag_eval(kps, hc, xm) : fk.kdiag(xm);
+      const double kss = TAB ? km[0] : (KID == KID_GENERIC) ? kdiag_eval(kps, hc, xm) : fk.kdiag(xm);
       const double nanv = __longlong_as_double(0x7ff8000000000000LL);
       a.mean[win * M + m] = bad ? nanv : ms;
       const double vv = fmax(kss - vs, CNGP_VAR_FLOOR) + noise;

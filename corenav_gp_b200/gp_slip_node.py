@@ -65,6 +65,19 @@ def context(device: int = 0) -> GpContext:
     return _ctx
 
 
+class NotPositiveDefiniteError(ArithmeticError):
+    """Ky of a window is not positive definite (NaN slip samples, a bad user-supplied theta).  In the reference GPy
+    raises LinAlgError inside the callback and nothing is published (gp_slip_node.py:35-36); the C++ twin
+    gp_slip_predict throws on the same condition."""
+
+
+def _raise_on_failed(status) -> None:
+    bad = np.flatnonzero(np.asarray(status) < 0)
+    if bad.size:
+        raise NotPositiveDefiniteError(f"GP window(s) {bad.tolist()[:8]} not positive definite (status "
+                                       f"{np.asarray(status)[bad].tolist()[:8]}): nothing published")
+
+
 def callback(data, theta=None, kernel: str = KERNEL) -> GP_Output:
     """gp_slip_node.callback: one GP_Input window in, one GP_Output message out (also handed to `pub`).
 
@@ -73,6 +86,7 @@ def callback(data, theta=None, kernel: str = KERNEL) -> GP_Output:
     X = np.asarray(data.time_array, dtype=np.float64).reshape(1, -1)
     Y = np.asarray(data.slip_array, dtype=np.float64).reshape(1, -1)
     mean, sigma, status = context().gp_slip(kernel, X, Y, theta=theta, horizon=HORIZON)
+    _raise_on_failed(status)
     msg_out = GP_Output()
     msg_out.mean = mean[0]
     msg_out.sigma = sigma[0]
@@ -85,6 +99,7 @@ def callback_batch(windows: Sequence, theta=None, kernel: str = KERNEL) -> List[
     X = np.stack([np.asarray(w.time_array, dtype=np.float64) for w in windows])
     Y = np.stack([np.asarray(w.slip_array, dtype=np.float64) for w in windows])
     mean, sigma, status = context().gp_slip(kernel, X, Y, theta=theta, horizon=HORIZON)
+    _raise_on_failed(status)
     return [GP_Output(mean=mean[b], sigma=sigma[b]) for b in range(len(windows))]
 
 
@@ -100,7 +115,7 @@ def callback_bytes(serialized: bytes, theta=None, kernel: str = KERNEL, framed: 
         serialized = body
     msg = wire.deserialize_gp_input(serialized)
     out = callback(GP_Input(time_array=msg.time_array, slip_array=msg.slip_array), theta=theta, kernel=kernel)
-    reply = wire.serialize(wire.GPOutput(wire.Header(msg.header.seq, msg.header.stamp, msg.header.frame_id),
+    reply = wire.serialize(wire.GPOutput(wire.Header(msg.header.seq, msg.header.stamp, msg.header.frame_id, msg.header.secs, msg.header.nsecs),
                                          np.asarray(out.mean), np.asarray(out.sigma)))
     return wire.frame(reply) if framed else reply
 

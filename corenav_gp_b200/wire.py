@@ -15,6 +15,7 @@ import hashlib
 import math
 import struct
 from dataclasses import dataclass, field
+from typing import Optional
 
 import numpy as np
 
@@ -61,9 +62,15 @@ def md5sum(name: str) -> str:
 
 @dataclass
 class Header:
+    """std_msgs/Header.  `stamp` (seconds, float64) is the convenient view; `secs` / `nsecs` hold the integer pair a
+    message arrived with.  A float64 at epoch scale resolves ~240 ns, so re-deriving the pair from the float can change
+    nsecs: serialisation re-uses the integer pair whenever `stamp` still equals the float it was decoded to, which
+    makes deserialise -> serialise byte-exact (ExactTime matching, republishing)."""
     seq: int = 0
     stamp: float = 0.0
     frame_id: str = ""
+    secs: Optional[int] = field(default=None, compare=False)
+    nsecs: Optional[int] = field(default=None, compare=False)
 
 
 @dataclass
@@ -100,7 +107,10 @@ def stamp_to_ros(t: float):
 
 
 def _put_header(h: Header) -> bytes:
-    s, ns = stamp_to_ros(h.stamp)
+    if h.secs is not None and h.nsecs is not None and h.stamp == h.secs + 1e-9 * h.nsecs:
+        s, ns = int(h.secs), int(h.nsecs)          # untouched since it was decoded: keep the exact pair
+    else:
+        s, ns = stamp_to_ros(h.stamp)
     fid = h.frame_id.encode()
     return struct.pack("<IIII", h.seq, s, ns, len(fid)) + fid
 
@@ -110,7 +120,7 @@ def _get_header(b: memoryview, at: int):
     at += 16
     if at + k > len(b):
         raise ValueError("truncated message")
-    return Header(seq, s + 1e-9 * ns, bytes(b[at:at + k]).decode()), at + k
+    return Header(seq, s + 1e-9 * ns, bytes(b[at:at + k]).decode(), secs=s, nsecs=ns), at + k
 
 
 def _put_vec(v) -> bytes:

@@ -87,8 +87,15 @@ typedef struct cngp_config {
   int32_t jitter_retry;      /* 0: a non-PD window gets status < 0 and NaN outputs; 1: GPy jitchol ladder
                                 (mean(diag)*1e-6, x10, 5 tries) - status = tries used */
   int64_t scratch_bytes;     /* device scratch for factors (0 = default 2 GiB); windows are processed in chunks */
-  int32_t reserved[8];
+  int32_t precision;         /* CNGP_PRECISION_F64 (default; 1e-9 parity) or CNGP_PRECISION_F32 (1e-4): the predictive
+                                mean / variance phase of cngp_predict_batch / cngp_gp_slip_batch runs on the TF32 tensor
+                                cores with the 3xTF32 split (FP32-level accuracy); factorisation, LML and every other
+                                entry point stay FP64.  Arrays at the ABI are double in both modes. */
+  int32_t reserved[7];
 } cngp_config;
+
+#define CNGP_PRECISION_F64 0
+#define CNGP_PRECISION_F32 1
 
 void cngp_default_config(cngp_config* cfg);
 int cngp_create(const cngp_config* cfg, cngp_ctx** out);
@@ -98,6 +105,8 @@ int cngp_sync(cngp_ctx* ctx);
 /* Make the context launch on an existing cudaStream_t (e.g. torch's current stream; 0 is the legacy default
  * stream), or back on the context's own non-blocking stream when use_own != 0. */
 int cngp_set_stream(cngp_ctx* ctx, void* cuda_stream, int32_t use_own);
+/* Switch the precision mode of an existing context (see cngp_config.precision). */
+int cngp_set_precision(cngp_ctx* ctx, int32_t precision);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t cngp_launch_count(cngp_ctx* ctx);
 int cngp_version(void);

@@ -106,13 +106,15 @@ inline double stamp_from_ros(uint32_t sec, uint32_t nsec) { return (double)sec +
 
 inline void put(Writer& w, const core_nav::Header& h) {
   uint32_t s, ns;
-  stamp_to_ros(h.stamp, s, ns);
+  if (h.stamp_raw && h.stamp == stamp_from_ros(h.stamp_sec, h.stamp_nsec)) { s = h.stamp_sec; ns = h.stamp_nsec; }   // byte-exact round trip
+  else stamp_to_ros(h.stamp, s, ns);
   w.u32(h.seq); w.u32(s); w.u32(ns); w.str(h.frame_id);
 }
 inline void get(Reader& r, core_nav::Header& h) {
   h.seq = r.u32();
   const uint32_t s = r.u32(), ns = r.u32();
   h.stamp = stamp_from_ros(s, ns);
+  h.stamp_sec = s; h.stamp_nsec = ns; h.stamp_raw = true;
   h.frame_id = r.str();
 }
 

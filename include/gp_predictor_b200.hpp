@@ -28,8 +28,12 @@
 namespace core_nav {
 struct Header {
   uint32_t seq = 0;
-  double stamp = 0.0;
+  double stamp = 0.0;          // seconds (ros::Time::toSec); the convenient view
   std::string frame_id;
+  // the integer pair the message arrived with (cngp_wire.hpp).  A double at epoch scale resolves ~240 ns, so the pair
+  // cannot be recovered from `stamp`; the serialiser re-uses it while `stamp` still equals the double it decoded to.
+  uint32_t stamp_sec = 0, stamp_nsec = 0;
+  bool stamp_raw = false;
 };
 struct GP_Input {   // core_navigation/msg/GP_Input.msg:1-3
   Header header;

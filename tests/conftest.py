@@ -26,3 +26,12 @@ def slipval():
     import numpy as np
     d = np.loadtxt(os.path.join(ROOT, "tests", "golden", "slipVal.csv"), delimiter=",")
     return d[:, 0], d[:, 1]
+
+
+@pytest.fixture(scope="session")
+def gp_ctx32():
+    """FP32-mode context (north_star: 1e-4): variance phase as 3xTF32 on the tensor cores."""
+    from corenav_gp_b200.api import GpContext
+    ctx = GpContext(device=0, precision="f32")
+    yield ctx
+    ctx.close()

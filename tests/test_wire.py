@@ -144,3 +144,26 @@ def test_wire_to_callback_to_wire(monkeypatch):
     assert wire.unframe(framed) == (reply, len(reply) + 4)
     with pytest.raises(ValueError):
         node.callback_bytes(wire.frame(wire.serialize(gi))[:-1], framed=True)
+
+
+def test_epoch_scale_stamp_round_trips_byte_exact():
+    """A float64 at epoch scale resolves ~240 ns: deserialise -> serialise must keep the integer (secs, nsecs) pair."""
+    import struct
+    body = struct.pack("<IIII", 7, 1760716800, 123456789, 4) + b"base" + struct.pack("<I", 0) + struct.pack("<I", 0)
+    m = wire.deserialize_gp_input(body)
+    assert (m.header.secs, m.header.nsecs) == (1760716800, 123456789)
+    assert wire.serialize(m) == body                                      # exact pair kept
+    assert wire.stamp_to_ros(m.header.stamp)[1] != 123456789              # ... which the float alone cannot give back
+    m.header.stamp += 1.0                                                 # an edited stamp is re-derived from the float
+    assert struct.unpack_from("<II", wire.serialize(m), 4)[0] == 1760716801
+
+
+def test_output_buffers_are_never_silently_replaced():
+    from corenav_gp_b200.api import CngpError, _Arg
+    import numpy as np
+    ok = np.empty((3, 4))
+    assert _Arg(ok, np.float64, False, output=True).ptr == ok.ctypes.data
+    for bad in (np.empty((3, 4), dtype=np.float32), np.empty((4, 6))[:, ::2], [0.0] * 4):
+        with pytest.raises(CngpError):
+            _Arg(bad, np.float64, False, output=True)
+    assert _Arg(np.empty((4, 6))[:, ::2], np.float64, False).keep.flags.c_contiguous       # inputs are coerced

@@ -1,5 +1,5 @@
 """Small driver for ncu captures: a few device-resident predict steps of the bench workload.
-usage: python tools/prof_predict.py [B] [N] [M] [steps] [kernel]"""
+usage: python tools/prof_predict.py [B] [N] [M] [steps] [kernel] [f64|f32]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,7 +11,8 @@ N = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 M = int(sys.argv[3]) if len(sys.argv) > 3 else 600
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 kern = sys.argv[5] if len(sys.argv) > 5 else "rbf+stdperiodic"
-ctx = GpContext(0)
+prec = sys.argv[6] if len(sys.argv) > 6 else "f64"
+ctx = GpContext(0, precision=prec)
 x, y = syn.slip_windows(0, B, N)
 xs = syn.test_grid(x[0], M)
 th = syn.theta_for(kern)
