@@ -36,7 +36,7 @@ struct LlhConst {
 
 // Deterministic sin / cos: Cody-Waite reduction by pi/2 in three fma steps, then the classic degree-13 / 14 minimax
 // polynomials on [-pi/4, pi/4] as fma Horner chains.  Only IEEE-exact operations in a fixed order (this TU is built with
-// -fmad=false), so the C oracle (oracle/stop_oracle.c, trig_mode = 1, built with -ffp-contract=off) returns the same bits
+// -fmad=false), so the C oracle (its trig_mode = 1, built with -ffp-contract=off) returns the same bits
 // and the stop decision is reproducible at a 0-ulp margin; within 1 ulp of libm / libdevice.  tan = sin / cos.
 __device__ __forceinline__ void det_sincos(double x, double& sn, double& cs) {
   const double k = rint(x * 6.36619772367581382433e-01);
@@ -199,6 +199,309 @@ __device__ __forceinline__ bool obs_cannot_trigger(const ObsBound& o, double dl,
   return o.usable && dl < 0.1 && (bound * (1.0 + 1e-9) + 1e-6 < thresh);     // NaN compares false: exact path
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core look-ahead.  One FP64 tensor-core instruction  mma.sync.m8n8k4.f64  returns, bit for bit, the ascending-k
+// chain of fma  d = fma(a3,b3, fma(a2,b2, fma(a1,b1, fma(a0,b0,c))))  (tools/dmma_semantics.cu: 1 280 000 of 1 280 000
+// outputs identical on B200; descending / pairwise / mul+add orders do not match).  An ascending-index fma chain starting
+// from 0 is exactly how the C oracle forms every dot product of the look-ahead, so the 15 x 15 algebra can run on the
+// FP64 tensor pipe - matrices zero-padded to 16 x 16 = 2 x 2 tiles, a 15-term chain = four k4 instructions whose 16th
+// term is fma(0, 0, acc) = acc - and still reproduce (triggered, i, step, xy_err) bit for bit.
+//
+// One warp per window.  Matrices live in shared memory row-major with a leading dimension of 20 doubles (12 for the
+// 16 x 4 ones): with that stride the A-fragment loads M[8 ri + g][4 ks + t], the B-fragment loads M[4 ks + t][8 ci + g]
+// and the 16-byte D-fragment stores M[8 ri + g][8 ci + 2t .. +1] all hit every bank pair exactly twice per warp - the
+// minimum for 8-byte accesses.  The fragments of the constant operands (STM as A and, transposed, as B; Q as accumulator
+// fragments; H) stay in registers for the whole window.  A propagation step is 32 instructions (F P, then (F P) F' + Q),
+// an update 64 (P H', H P, S, K, I - K H, K R, (I-KH) P, (..)(I-KH)' + (K R) K'), against ~6000 scalar fma with two
+// shared-memory loads each in the scalar kernels below.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TC_LD = 20, TC_LD4 = 12;
+constexpr int TC_P = 0, TC_T = 320, TC_A = 640, TC_H = 960, TC_HP = 1120, TC_PHT = 1280, TC_K = 1472, TC_KR = 1664,
+              TC_S = 1856, TC_R = 1872, TC_WS = 1888;     // doubles per warp
+constexpr int TC_WARPS = 8;
+
+__device__ __forceinline__ void dmma(double2& d, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d.x), "+d"(d.y) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double pick16(const double* v, int idx) {   // v is a register array: unrolled selects
+  double r = v[0];
+#pragma unroll
+  for (int e = 1; e < 16; ++e) r = (idx == e) ? v[e] : r;
+  return r;
+}
+
+__global__ void __launch_bounds__(TC_WARPS * 32) zupt_lookahead_tc_kernel(const LookaheadArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + w;
+  if (b >= a.B) return;
+  const int g = lane >> 2, t = lane & 3;
+  double* ws = smem + (long long)w * TC_WS;
+  double *Ps = ws + TC_P, *Ts = ws + TC_T, *As = ws + TC_A, *Hs = ws + TC_H, *HPs = ws + TC_HP, *PHts = ws + TC_PHT,
+         *Ks = ws + TC_K, *KRs = ws + TC_KR, *Ss = ws + TC_S, *Rs = ws + TC_R;
+  const cngp_stop_config& cfg = a.cfg;
+  const int pw = a.per_window;
+  const double* gP = a.P + ((pw & CNGP_PERWIN_P) ? b * 225 : 0);
+  const double* gQ = a.Q + ((pw & CNGP_PERWIN_Q) ? b * 225 : 0);
+  const double* gF = a.STM + ((pw & CNGP_PERWIN_STM) ? b * 225 : 0);
+  const double* gH = a.Hvec + ((pw & CNGP_PERWIN_H) ? b * 60 : 0);
+  const double* gpos = a.pos + ((pw & CNGP_PERWIN_POS) ? b * 3 : 0);
+
+  for (int i = lane; i < TC_WS; i += 32) ws[i] = 0.0;           // zero padding everywhere
+  __syncwarp();
+  for (int i = lane; i < 225; i += 32) {
+    const int rr = i / 15, cc = i % 15;
+    Ps[rr * TC_LD + cc] = gP[i];
+    Ts[rr * TC_LD + cc] = gF[i];                                // the STM passes through T's storage on its way to registers
+  }
+  for (int i = lane; i < 60; i += 32) {
+    const int rr = i / 15, cc = i % 15;
+    Hs[rr * TC_LD + cc] = gH[cfg.fix_h_packing ? rr * 15 + cc : rr * 4 + cc];   // gp_predictor.cpp:38-42 aliasing index
+  }
+  __syncwarp();
+  // constant fragments.  Ff[ri][ks] = F[8ri+g][4ks+t]: A fragment of F, and B fragment of F' for column tile ri.
+  double Ff[2][4], Hf[4], Hb[2];
+  double2 Qd[2][2];
+#pragma unroll
+  for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) Ff[ri][ks] = Ts[(8 * ri + g) * TC_LD + 4 * ks + t];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) Hf[ks] = Hs[g * TC_LD + 4 * ks + t];       // A fragment of H (rows 4..7 are padding)
+#pragma unroll
+  for (int ci = 0; ci < 2; ++ci) Hb[ci] = Hs[t * TC_LD + 8 * ci + g];       // B fragment of H as the 4 x 16 right factor
+#pragma unroll
+  for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) {
+      const int rr = 8 * ri + g, c0 = 8 * ci + 2 * t;
+      Qd[ri][ci].x = (rr < 15 && c0 < 15) ? gQ[rr * 15 + c0] : 0.0;
+      Qd[ri][ci].y = (rr < 15 && c0 + 1 < 15) ? gQ[rr * 15 + c0 + 1] : 0.0;
+    }
+  const double lat = gpos[0], lon = gpos[1], hgt = gpos[2];
+  const LlhConst lk = llh_prepare(cfg);
+  double enu0[3];
+  llh_to_enu_dev(lat, lon, hgt, lk, cfg, enu0);
+  const ObsBound ob = obs_prepare(lat, lon, hgt, cfg);
+  __syncwarp();
+
+  const double* mean = a.mean + b * a.M;
+  const double* sigma = a.sigma + b * a.M;
+  const int nsteps = cfg.ratio * a.M;
+  int i_upd = 0, trig = 0, step = nsteps;
+  double xy = 0.0;
+  // R1 of gp_predictor.cpp:84-87 seen from this lane: row g (as the left factor), rows 2t, 2t+1 (as the right factor)
+  const double it = 1 / cfg.track;
+  auto r1 = [&](int row, int k) -> double {
+    return row == 0 ? (k < 2 ? 0.5 : 0.0) : row == 1 ? (k == 0 ? it : k == 1 ? -it : 0.0) : (row == k && row < 4 ? 1.0 : 0.0);
+  };
+
+  for (int slip_i = 0; slip_i < nsteps; ++slip_i) {
+    // ---- P = F P F' + Q ----
+    {
+      double2 Td[2][2];
+#pragma unroll
+      for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) Td[ri][ci] = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const double b0 = Ps[(4 * ks + t) * TC_LD + g], b1 = Ps[(4 * ks + t) * TC_LD + 8 + g];
+        dmma(Td[0][0], Ff[0][ks], b0); dmma(Td[0][1], Ff[0][ks], b1);
+        dmma(Td[1][0], Ff[1][ks], b0); dmma(Td[1][1], Ff[1][ks], b1);
+      }
+#pragma unroll
+      for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci)
+          *reinterpret_cast<double2*>(Ts + (8 * ri + g) * TC_LD + 8 * ci + 2 * t) = Td[ri][ci];
+      __syncwarp();
+      double2 Pd[2][2];
+#pragma unroll
+      for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) Pd[ri][ci] = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const double a0 = Ts[g * TC_LD + 4 * ks + t], a1 = Ts[(8 + g) * TC_LD + 4 * ks + t];
+        dmma(Pd[0][0], a0, Ff[0][ks]); dmma(Pd[0][1], a0, Ff[1][ks]);
+        dmma(Pd[1][0], a1, Ff[0][ks]); dmma(Pd[1][1], a1, Ff[1][ks]);
+      }
+#pragma unroll
+      for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci)
+          *reinterpret_cast<double2*>(Ps + (8 * ri + g) * TC_LD + 8 * ci + 2 * t) =
+              make_double2(Pd[ri][ci].x + Qd[ri][ci].x, Pd[ri][ci].y + Qd[ri][ci].y);
+      __syncwarp();
+    }
+    if (slip_i % cfg.ratio == 0) {
+      // ---- UT -> R_IP (this lane's two entries R[g][2t], R[g][2t+1]; only g < 4, t < 2 are real) ----
+      {
+        const double mu = mean[i_upd], sg = sigma[i_upd];
+        const double chi0 = cfg.v_nom / (1.0 - mu);
+        const double chi1 = cfg.v_nom / (1.0 - (mu + sg));
+        const double chi2 = cfg.v_nom / (1.0 - (mu - sg));
+        const double est = (chi0 + chi1 + chi2) / 3.0;
+        const double cov = ((chi0 - est) * (chi0 - est) + (chi1 - est) * (chi1 - est) + (chi2 - est) * (chi2 - est)) / 3.0;
+        const double c2 = cov * cov;
+        const double fa = cfg.floor_a * cfg.floor_a, fb = cfg.floor_b * cfg.floor_b;
+        const double R2[4] = {fmax(fa, c2), fmax(fa, c2), fmax(fb, c2), fb};
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double bm = (cfg.scale * r1(g, k)) * R2[k];
+          acc0 = fma(bm, r1(2 * t, k), acc0);
+          acc1 = fma(bm, r1(2 * t + 1, k), acc1);
+        }
+        if (g < 4 && t < 2) { Rs[g * 4 + 2 * t] = acc0; Rs[g * 4 + 2 * t + 1] = acc1; }
+      }
+      // ---- P H' (16 x 8) and H P (8 x 16) ----
+      {
+        double2 D0 = make_double2(0.0, 0.0), D1 = D0, E0 = D0, E1 = D0;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const double a0 = Ps[g * TC_LD + 4 * ks + t], a1 = Ps[(8 + g) * TC_LD + 4 * ks + t];
+          dmma(D0, a0, Hf[ks]); dmma(D1, a1, Hf[ks]);                       // P H': B fragment of H' = A fragment of H
+          const double b0 = Ps[(4 * ks + t) * TC_LD + g], b1 = Ps[(4 * ks + t) * TC_LD + 8 + g];
+          dmma(E0, Hf[ks], b0); dmma(E1, Hf[ks], b1);                       // H P
+        }
+        *reinterpret_cast<double2*>(PHts + g * TC_LD4 + 2 * t) = D0;
+        *reinterpret_cast<double2*>(PHts + (8 + g) * TC_LD4 + 2 * t) = D1;
+        *reinterpret_cast<double2*>(HPs + g * TC_LD + 2 * t) = E0;
+        *reinterpret_cast<double2*>(HPs + g * TC_LD + 8 + 2 * t) = E1;
+      }
+      __syncwarp();
+      // ---- S = (H P) H' + R ----
+      {
+        double2 Sd = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) dmma(Sd, HPs[g * TC_LD + 4 * ks + t], Hf[ks]);
+        if (g < 4 && t < 2) {
+          Ss[g * 4 + 2 * t] = Sd.x + Rs[g * 4 + 2 * t];
+          Ss[g * 4 + 2 * t + 1] = Sd.y + Rs[g * 4 + 2 * t + 1];
+        }
+      }
+      __syncwarp();
+      // ---- K = (P H') S^-1,  I - K H,  K R ----
+      {
+        double Sl[16], Sil[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) Sl[e] = Ss[e];
+        inv4(Sl, Sil);
+        const double sib = g < 4 ? pick16(Sil, t * 4 + g) : 0.0;            // B fragment of S^-1: Si[t][g]
+        double2 K0 = make_double2(0.0, 0.0), K1 = K0;
+        dmma(K0, PHts[g * TC_LD4 + t], sib);
+        dmma(K1, PHts[(8 + g) * TC_LD4 + t], sib);
+        *reinterpret_cast<double2*>(Ks + g * TC_LD4 + 2 * t) = K0;
+        *reinterpret_cast<double2*>(Ks + (8 + g) * TC_LD4 + 2 * t) = K1;
+      }
+      __syncwarp();
+      double Af[2][4];     // A fragments of I - K H, kept for both products below
+      double Kf[2];        // A fragments of K (= B fragments of K')
+      {
+        Kf[0] = Ks[g * TC_LD4 + t]; Kf[1] = Ks[(8 + g) * TC_LD4 + t];
+        double2 Ad[2][2];
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci) {
+            Ad[ri][ci] = make_double2(0.0, 0.0);
+            dmma(Ad[ri][ci], Kf[ri], Hb[ci]);
+            const int rr = 8 * ri + g, c0 = 8 * ci + 2 * t;
+            Ad[ri][ci].x = ((rr == c0 && rr < 15) ? 1.0 : 0.0) - Ad[ri][ci].x;
+            Ad[ri][ci].y = ((rr == c0 + 1 && rr < 15) ? 1.0 : 0.0) - Ad[ri][ci].y;
+            *reinterpret_cast<double2*>(As + rr * TC_LD + c0) = Ad[ri][ci];
+          }
+        const double rb = g < 4 ? Rs[t * 4 + g] : 0.0;                      // B fragment of R: R[t][g]
+        double2 KR0 = make_double2(0.0, 0.0), KR1 = KR0;
+        dmma(KR0, Kf[0], rb);
+        dmma(KR1, Kf[1], rb);
+        *reinterpret_cast<double2*>(KRs + g * TC_LD4 + 2 * t) = KR0;
+        *reinterpret_cast<double2*>(KRs + (8 + g) * TC_LD4 + 2 * t) = KR1;
+      }
+      __syncwarp();
+      // ---- Joseph form: P = ((I-KH) P) (I-KH)' + (K R) K' ----
+      {
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) Af[ri][ks] = As[(8 * ri + g) * TC_LD + 4 * ks + t];
+        double2 Td[2][2];
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci) Td[ri][ci] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const double b0 = Ps[(4 * ks + t) * TC_LD + g], b1 = Ps[(4 * ks + t) * TC_LD + 8 + g];
+          dmma(Td[0][0], Af[0][ks], b0); dmma(Td[0][1], Af[0][ks], b1);
+          dmma(Td[1][0], Af[1][ks], b0); dmma(Td[1][1], Af[1][ks], b1);
+        }
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci)
+            *reinterpret_cast<double2*>(Ts + (8 * ri + g) * TC_LD + 8 * ci + 2 * t) = Td[ri][ci];
+        __syncwarp();
+        double2 Pd[2][2], Gd[2][2];
+        const double kr0 = KRs[g * TC_LD4 + t], kr1 = KRs[(8 + g) * TC_LD4 + t];
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci) {
+            Pd[ri][ci] = make_double2(0.0, 0.0);
+            Gd[ri][ci] = make_double2(0.0, 0.0);
+            dmma(Gd[ri][ci], ri ? kr1 : kr0, Kf[ci]);
+          }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const double a0 = Ts[g * TC_LD + 4 * ks + t], a1 = Ts[(8 + g) * TC_LD + 4 * ks + t];
+          dmma(Pd[0][0], a0, Af[0][ks]); dmma(Pd[0][1], a0, Af[1][ks]);
+          dmma(Pd[1][0], a1, Af[0][ks]); dmma(Pd[1][1], a1, Af[1][ks]);
+        }
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci)
+            *reinterpret_cast<double2*>(Ps + (8 * ri + g) * TC_LD + 8 * ci + 2 * t) =
+                make_double2(Pd[ri][ci].x + Gd[ri][ci].x, Pd[ri][ci].y + Gd[ri][ci].y);
+        __syncwarp();
+      }
+      ++i_upd;
+    }
+    // ---- error observer ----
+    const double dl3 = 3.0 * sqrt(fabs(Ps[6 * TC_LD + 6])), dm3 = 3.0 * sqrt(fabs(Ps[7 * TC_LD + 7])),
+                 dh3 = 3.0 * sqrt(fabs(Ps[8 * TC_LD + 8]));
+    if (slip_i + 1 < nsteps && obs_cannot_trigger(ob, dl3, dm3, dh3, cfg.thresh)) continue;
+    const double lat3 = lat + dl3;
+    const double lon3 = lon + dm3;
+    const double h3 = hgt + dh3;
+    double tsn, tcs;                               // lane 0: latitude, lane 1: longitude
+    det_sincos(lane == 0 ? lat3 : lon3, tsn, tcs);
+    const double sp = __shfl_sync(0xffffffffu, tsn, 0), cp = __shfl_sync(0xffffffffu, tcs, 0),
+                 sl = __shfl_sync(0xffffffffu, tsn, 1), cl = __shfl_sync(0xffffffffu, tcs, 1);
+    const double tp = sp / cp;
+    double enu3[3];
+    llh_to_enu_trig(sp, cp, tp, sl, cl, h3, lk, cfg, enu3);
+    const double dx = enu3[0] - enu0[0], dy = enu3[1] - enu0[1];
+    xy = sqrt(dx * dx + dy * dy);
+    if (xy > cfg.thresh) { trig = 1; step = slip_i; break; }
+  }
+  if (lane == 0) {
+    a.triggered[b] = trig;
+    a.i_stop[b] = i_upd;
+    a.step_stop[b] = step;
+    a.xy_err[b] = xy;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Scalar kernels (round 1): the same algebra as explicit fma chains.  Kept as an independent implementation of the same
+// bits - tests/test_gpu_lookahead.py runs all three on one batch and demands identical xy_err - and selectable with
+// CNGP_LOOKAHEAD_KERNEL = warp | cta.
+// ---------------------------------------------------------------------------------------------------------------------
 // per-warp shared-memory working set (doubles)
 constexpr int LA_P = 0, LA_T = 225, LA_A = 450, LA_PHT = 675, LA_K = 735, LA_KR = 795, LA_S = 855, LA_SI = 871,
               LA_R = 887, LA_F = 903, LA_Q = 1128, LA_H = 1353, LA_HP = 1413, LA_WS = 1473 + 3;  // padded to an even count
@@ -624,8 +927,21 @@ extern "C" int cngp_launch_lookahead(const double* mean, const double* sigma, lo
     cudaFuncSetAttribute(zupt_lookahead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
-  const char* force = getenv("CNGP_LOOKAHEAD_KERNEL");     // "warp" / "cta": tests exercise both on the same batch
-  const bool cta = force ? force[0] == 'c' : B <= LA_CTA_MAX_B;
+  const char* force = getenv("CNGP_LOOKAHEAD_KERNEL");     // "tc" (default) / "warp" / "cta": tests run all on one batch
+  if (!force || force[0] == 't') {
+    // few windows: one warp per CTA so that they spread over the SMs; many: eight warps per CTA
+    const int wpc = B <= 4 * 148 ? 1 : TC_WARPS;
+    const size_t tsm = (size_t)TC_WARPS * TC_WS * sizeof(double);
+    static bool tc_attr = false;
+    if (!tc_attr) {
+      cudaFuncSetAttribute(zupt_lookahead_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+      tc_attr = true;
+    }
+    const long long grid = (B + wpc - 1) / wpc;
+    zupt_lookahead_tc_kernel<<<(unsigned)grid, wpc * 32, (size_t)wpc * TC_WS * sizeof(double), stream>>>(a);
+    return (int)cudaGetLastError();
+  }
+  const bool cta = force[0] == 'c';
   if (cta) {
     zupt_lookahead_cta_kernel<<<(unsigned)B, LA_CTA_THREADS, LA_WS * sizeof(double), stream>>>(a);
     return (int)cudaGetLastError();

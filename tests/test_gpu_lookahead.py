@@ -100,10 +100,11 @@ def test_lookahead_fix_h_packing_and_ratio(gp_ctx):
             assert np.array_equal(out[k], ref[k]), (k, ratio)
 
 
-@pytest.mark.parametrize("kernel", ["warp", "cta"])
+@pytest.mark.parametrize("kernel", ["tc", "warp", "cta"])
 def test_both_kernel_shapes_match_the_oracle(gp_ctx, monkeypatch, kernel):
-    """Large batches run one warp per window, small ones (<= 592 windows, the reference's single callback) one CTA per
-    window; both keep the oracle's fma order, so the decisions - and the two kernels' xy_err - are identical."""
+    """Three implementations of the same bits: the tensor-core kernel (default; one DMMA = an ascending fma chain, see
+    tools/dmma_semantics.cu) and the two scalar kernels of round 1 (one warp / one CTA per window).  All keep the
+    oracle's fma order, so the decisions - and every kernel's xy_err - are identical."""
     monkeypatch.setenv("CNGP_LOOKAHEAD_KERNEL", kernel)
     B, M = 96, 260
     mean, sigma = gp_outputs(B, M, seed=5)
@@ -113,9 +114,10 @@ def test_both_kernel_shapes_match_the_oracle(gp_ctx, monkeypatch, kernel):
     assert 0 < ref["triggered"].sum()
     for k in ("triggered", "i_stop", "step_stop", "xy_err"):
         assert np.array_equal(out[k], ref[k]), k
-    monkeypatch.setenv("CNGP_LOOKAHEAD_KERNEL", "cta" if kernel == "warp" else "warp")
-    other = gp_ctx.zupt_lookahead(mean, sigma, ctx["P"], ctx["Q"], ctx["STM"], ctx["Hvec"], ctx["pos"])
-    assert np.array_equal(out["xy_err"], other["xy_err"]) and np.array_equal(out["step_stop"], other["step_stop"])
+    for k2 in ("tc", "warp", "cta"):
+        monkeypatch.setenv("CNGP_LOOKAHEAD_KERNEL", k2)
+        other = gp_ctx.zupt_lookahead(mean, sigma, ctx["P"], ctx["Q"], ctx["STM"], ctx["Hvec"], ctx["pos"])
+        assert np.array_equal(out["xy_err"], other["xy_err"]) and np.array_equal(out["step_stop"], other["step_stop"]), k2
 
 
 def test_dense_stm_takes_the_general_propagation(gp_ctx, monkeypatch):
@@ -126,7 +128,7 @@ def test_dense_stm_takes_the_general_propagation(gp_ctx, monkeypatch):
     F = ctx["STM"].reshape(15, 15).copy()
     F[10, 2] = 1e-4                                        # couples a bias state: rows 9..14 are no longer unit rows
     ref = so.lookahead_batch(mean, sigma, ctx["P"], ctx["Q"], F.reshape(225), ctx["Hvec"], ctx["pos"], ocfg())
-    for kernel in ("warp", "cta"):
+    for kernel in ("tc", "warp", "cta"):
         monkeypatch.setenv("CNGP_LOOKAHEAD_KERNEL", kernel)
         out = gp_ctx.zupt_lookahead(mean, sigma, ctx["P"], ctx["Q"], F.reshape(225), ctx["Hvec"], ctx["pos"])
         for k in ("triggered", "i_stop", "step_stop"):
@@ -150,3 +152,16 @@ def test_lookahead_matches_the_reference_binary(gp_ctx):
             r = rg.gp_callback(g["mean"][b], g["sigma"][b], g["P"][b], g["Q"][b], g["STM"][b], g["Hvec"][b], g["pos"][b])
             assert r["triggered"] == bool(out["triggered"][b]) and r["i_stop"] == out["i_stop"][b]
             assert abs(r["xy_err"] - out["xy_err"][b]) < 1e-9 * r["xy_err"]
+
+
+def test_tensor_core_kernel_many_windows_per_cta_and_monte_carlo_contexts(gp_ctx):
+    """More windows than 4 x 148 (eight warps per CTA), per-window P and Q of the Monte-Carlo fixture: some windows run
+    the whole horizon without a trigger, some trigger at step 0."""
+    B, M = 1500, 120
+    mean, sigma = gp_outputs(B, M, seed=12)
+    ctx = syn.monte_carlo_contexts(1000, B)
+    out = gp_ctx.zupt_lookahead(mean, sigma, ctx["P"], ctx["Q"], ctx["STM"], ctx["Hvec"], ctx["pos"])
+    ref = so.lookahead_batch(mean, sigma, ctx["P"], ctx["Q"], ctx["STM"], ctx["Hvec"], ctx["pos"], ocfg())
+    assert 0 < ref["triggered"].sum() < B
+    for k in ("triggered", "i_stop", "step_stop", "xy_err"):
+        assert np.array_equal(out[k], ref[k]), k
