@@ -20,7 +20,7 @@
 
 extern "C" int cngp_launch_lookahead(const double*, const double*, long long, int, const double*, const double*,
                                      const double*, const double*, const double*, int, const cngp_stop_config*, int*,
-                                     int*, int*, double*, cudaStream_t);
+                                     int*, int*, double*, unsigned long long*, cudaStream_t);
 extern "C" int cngp_launch_llh_to_enu(const double*, long long, const cngp_stop_config*, double*, cudaStream_t);
 extern "C" int cngp_launch_ekf_context(const double*, const double*, const double*, const double*, long long, double, double,
                                        double*, double*, double*, cudaStream_t);
@@ -802,8 +802,10 @@ extern "C" int cngp_zupt_lookahead_batch(cngp_ctx* ctx, const double* mean, cons
   if (!d_xy) d_xy = (double*)ctx->buf(13, sizeof(double) * (size_t)B);
   if (!d_step || !d_xy) return fail(ctx, CNGP_ERR_NOMEM, "lookahead: buffers");
   ctx->begin(CNGP_PROF_LOOKAHEAD);
+  unsigned long long* d_counter = (unsigned long long*)ctx->buf(17, 64);
+  if (!d_counter) return fail(ctx, CNGP_ERR_NOMEM, "lookahead: work counter");
   const int e = cngp_launch_lookahead(d_mean, d_sigma, B, M, d_P, d_Q, d_F, d_H, d_pos, per_window, &c, d_trig, d_i,
-                                      d_step, d_xy, ctx->stream);
+                                      d_step, d_xy, d_counter, ctx->stream);
   ctx->end();
   if (e) return fail(ctx, CNGP_ERR_CUDA, "lookahead launch: %s", cudaGetErrorString((cudaError_t)e));
   const int rc = st.finish();

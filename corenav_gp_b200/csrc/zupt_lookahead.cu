@@ -27,6 +27,7 @@ struct LookaheadArgs {
   int per_window;
   cngp_stop_config cfg;
   int* triggered; int* i_stop; int* step_stop; double* xy_err;
+  unsigned long long* next_window;   // tensor-core kernel: work counter (windows are claimed one at a time), or null
 };
 
 struct LlhConst {
@@ -217,8 +218,11 @@ __device__ __forceinline__ bool obs_cannot_trigger(const ObsBound& o, double dl,
 // shared-memory loads each in the scalar kernels below.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TC_LD = 20, TC_LD4 = 12;
-constexpr int TC_P = 0, TC_T = 320, TC_A = 640, TC_H = 960, TC_HP = 1120, TC_PHT = 1280, TC_K = 1472, TC_KR = 1664,
-              TC_S = 1856, TC_R = 1872, TC_WS = 1888;     // doubles per warp
+// Working set per warp (doubles).  Buffers with disjoint lifetimes share storage: I - K H lives where H P and P H' were
+// (both dead once K is formed), K R in the head of T (dead between the propagation and the Joseph products; it is pulled
+// into registers before T is written again).  11 KB per warp: two CTAs of eight warps per SM.
+constexpr int TC_P = 0, TC_T = 320, TC_KR = 320, TC_HP = 640, TC_PHT = 800, TC_A = 640, TC_K = 992, TC_H = 1184,
+              TC_S = 1344, TC_R = 1360, TC_WS = 1376;
 constexpr int TC_WARPS = 8;
 
 __device__ __forceinline__ void dmma(double2& d, double a, double b) {
@@ -231,13 +235,22 @@ __device__ __forceinline__ double pick16(const double* v, int idx) {   // v is a
   return r;
 }
 
-__global__ void __launch_bounds__(TC_WARPS * 32) zupt_lookahead_tc_kernel(const LookaheadArgs a) {
+__global__ void __launch_bounds__(TC_WARPS * 32, 2) zupt_lookahead_tc_kernel(const LookaheadArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + w;
-  if (b >= a.B) return;
   const int g = lane >> 2, t = lane & 3;
   double* ws = smem + (long long)w * TC_WS;
+  // Windows run anywhere between 1 and ratio * M steps (early exit at the trigger), so they are not dealt statically:
+  // every warp claims the next unclaimed window from a global counter until none is left.  (Without a counter - small
+  // batches, one warp per CTA - warp k of the grid takes window k.)
+  for (long long b = (long long)blockIdx.x * (blockDim.x >> 5) + w;; ) {
+  if (a.next_window) {
+    unsigned long long nb = 0;
+    if (lane == 0) nb = atomicAdd(a.next_window, 1ULL);
+    b = (long long)__shfl_sync(0xffffffffu, nb, 0);
+  }
+  if (b >= a.B) return;
+  __syncwarp();
   double *Ps = ws + TC_P, *Ts = ws + TC_T, *As = ws + TC_A, *Hs = ws + TC_H, *HPs = ws + TC_HP, *PHts = ws + TC_PHT,
          *Ks = ws + TC_K, *KRs = ws + TC_KR, *Ss = ws + TC_S, *Rs = ws + TC_R;
   const cngp_stop_config& cfg = a.cfg;
@@ -428,6 +441,8 @@ __global__ void __launch_bounds__(TC_WARPS * 32) zupt_lookahead_tc_kernel(const 
         for (int ri = 0; ri < 2; ++ri)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) Af[ri][ks] = As[(8 * ri + g) * TC_LD + 4 * ks + t];
+        const double kr0 = KRs[g * TC_LD4 + t], kr1 = KRs[(8 + g) * TC_LD4 + t];
+        __syncwarp();        // K R shares storage with T: every lane has its fragment before T is written
         double2 Td[2][2];
 #pragma unroll
         for (int ri = 0; ri < 2; ++ri)
@@ -446,7 +461,6 @@ __global__ void __launch_bounds__(TC_WARPS * 32) zupt_lookahead_tc_kernel(const 
             *reinterpret_cast<double2*>(Ts + (8 * ri + g) * TC_LD + 8 * ci + 2 * t) = Td[ri][ci];
         __syncwarp();
         double2 Pd[2][2], Gd[2][2];
-        const double kr0 = KRs[g * TC_LD4 + t], kr1 = KRs[(8 + g) * TC_LD4 + t];
 #pragma unroll
         for (int ri = 0; ri < 2; ++ri)
 #pragma unroll
@@ -495,6 +509,8 @@ __global__ void __launch_bounds__(TC_WARPS * 32) zupt_lookahead_tc_kernel(const 
     a.step_stop[b] = step;
     a.xy_err[b] = xy;
   }
+  if (!a.next_window) return;
+  }   // next claimed window
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -918,9 +934,10 @@ __global__ void llh_to_enu_kernel(const double* llh, long long n, cngp_stop_conf
 extern "C" int cngp_launch_lookahead(const double* mean, const double* sigma, long long B, int M, const double* P,
                                      const double* Q, const double* STM, const double* Hvec, const double* pos,
                                      int per_window, const cngp_stop_config* cfg, int* triggered, int* i_stop,
-                                     int* step_stop, double* xy_err, cudaStream_t stream) {
+                                     int* step_stop, double* xy_err, unsigned long long* work_counter,
+                                     cudaStream_t stream) {
   using namespace cngp;
-  LookaheadArgs a{mean, sigma, B, M, P, Q, STM, Hvec, pos, per_window, *cfg, triggered, i_stop, step_stop, xy_err};
+  LookaheadArgs a{mean, sigma, B, M, P, Q, STM, Hvec, pos, per_window, *cfg, triggered, i_stop, step_stop, xy_err, nullptr};
   const size_t smem = (size_t)LA_WARPS * LA_WS * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
@@ -935,9 +952,15 @@ extern "C" int cngp_launch_lookahead(const double* mean, const double* sigma, lo
     static bool tc_attr = false;
     if (!tc_attr) {
       cudaFuncSetAttribute(zupt_lookahead_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+      cudaFuncSetAttribute(zupt_lookahead_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // two CTAs per SM
       tc_attr = true;
     }
-    const long long grid = (B + wpc - 1) / wpc;
+    long long grid = (B + wpc - 1) / wpc;
+    if (wpc == TC_WARPS && work_counter && grid > 2 * 148) {     // persistent: two CTAs per SM claim windows dynamically
+      if (cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream) != cudaSuccess) return (int)cudaGetLastError();
+      a.next_window = work_counter;
+      grid = 2 * 148;
+    }
     zupt_lookahead_tc_kernel<<<(unsigned)grid, wpc * 32, (size_t)wpc * TC_WS * sizeof(double), stream>>>(a);
     return (int)cudaGetLastError();
   }
