@@ -49,6 +49,24 @@ def flops_per_window(N=N_TRAIN, M=M_TEST):
 # ----------------------------------------------------------------------------------------------------------------
 # CPU port (oracle) legs
 # ----------------------------------------------------------------------------------------------------------------
+def _cpu_worker_pointwise(args):
+    """The reference's own loop shape (gp_slip_node.py:47-50): one m.predict([[x]]) per test point."""
+    first, count = args
+    from threadpoolctl import threadpool_limits
+    from corenav_gp_b200 import synthetic as syn
+    from oracle import gp_oracle as go
+    with threadpool_limits(limits=1):
+        x, y = syn.slip_windows(first, count, N_TRAIN)
+        th = syn.theta_for(KERNEL)
+        e = go.KernelExpr(KERNEL)
+        acc = 0.0
+        for b in range(count):
+            xs = syn.test_grid(x[b], M_TEST)
+            mu, var = go.predict_pointwise(e, th[:-1], th[-1], x[b], y[b], xs)
+            acc += float(mu[0] + var[0])
+    return acc
+
+
 def _cpu_worker(args):
     first, count = args
     from threadpoolctl import threadpool_limits
@@ -66,15 +84,16 @@ def _cpu_worker(args):
     return acc
 
 
-def cpu_port_throughput(windows_per_core: int, cores: int):
+def cpu_port_throughput(windows_per_core: int, cores: int, worker=None):
     """Windows/s of the oracle port with `cores` worker processes (1 BLAS thread each)."""
     import multiprocessing as mp
+    worker = worker or _cpu_worker
     ctx = mp.get_context("fork")
     jobs = [(10_000_000 + i * windows_per_core, windows_per_core) for i in range(cores)]
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(0, 1)] * cores)           # warm the workers (imports, first BLAS call)
+        pool.map(worker, [(0, 1)] * cores)                # warm the workers (imports, first BLAS call)
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, jobs, chunksize=1)
+        pool.map(worker, jobs, chunksize=1)
         dt = time.perf_counter() - t0
     return windows_per_core * cores / dt, dt
 
@@ -300,13 +319,21 @@ def run_ours(args):
         var_flops = (fl["var"] + fl["mean"]) * B_PER_GPU
         fit_flops = (fl["chol"] + fl["alpha"]) * B_PER_GPU
         achieved = var_flops / (var_avg_ms * 1e-3) * 1e-12
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("gp_var_kernel_dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                traffic = tj.get("gp_var_kernel_dram_bytes_per_launch")
+                traffic_src = tj.get("source")
             except Exception:
                 traffic = None
+        dmma_peak = None
+        try:                                   # DMMA / DFMA issue micro-benchmark (tools/fp64_peak.cu), a second anchor
+            r = subprocess.run([os.path.join(ROOT, "tools", "fp64_peak")], capture_output=True, text=True, timeout=60)
+            dmma_peak = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception:
+            dmma_peak = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -319,6 +346,7 @@ def run_ours(args):
             "roofline": {
                 "bound": "fp64", "kernel": "gp_var_kernel", "achieved": achieved, "peak": peak_tflops,
                 "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic,
+                "traffic_source": traffic_src, "fp64_issue_peaks": dmma_peak,
                 "peak_source": "cuBLAS DGEMM 4096^3 (torch.matmul float64) measured live in this run, burst best-of-6; "
                                "MEASURED_PEAKS.json has no FP64 figure (profiles/fp64_peak_r01.json: DMMA issue peak 37.2)",
                 "algorithmic_flop_per_launch": var_flops, "avg_launch_ms": var_avg_ms,
@@ -347,12 +375,74 @@ def run_ours(args):
             except Exception:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": "failed: " + (r.stderr or r.stdout)[-200:]}
+    # ---- extra: the other BASELINE configs and the FP32 mode, device-timed, outside the headline's timed region ----
+    extra = None
+    if not args.no_extra:
+        extra = run_extra(ctx, torch, rank, world, (dx, dy, dxs, dth), out_dev)
+    if rank == 0:
+        if extra is not None:
+            line["extra"] = extra
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
     return 0
+
+
+def run_extra(ctx, torch, rank, world, dev_in, out_dev):
+    """Numbers for the configs the headline does not carry, so that the driver's records hold them (every rank takes
+    part: configs[3] is sharded over the ranks, configs[4] is factored block-cyclically over them):
+      configs[0]  one N=100 window, host buffers: ms per predict + look-ahead callback                 (rank 0)
+      configs[2]  Kernel Selection sweep, 64 candidates x 4096 windows, N=256: LML+gradient per second   (rank 0)
+      configs[3]  Monte-Carlo shard of 131072 windows per GPU, N=128: windows/s over all ranks
+      configs[4]  one N=32768 window, blocked Cholesky over all ranks: ms
+      fp32_mode   the headline workload in FP32 mode (3xTF32 variance phase): windows/s per GPU        (rank 0)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_configs as bc
+    import bench_large as bl
+    ex = {"configs": {}}
+    try:
+        if rank == 0:
+            ex["configs"]["configs[0]"] = bc.single(ctx)
+            ex["configs"]["configs[2]"] = bc.sweep(ctx, 1.0)
+            # FP32 mode on the headline workload
+            dx, dy, dxs, dth = dev_in
+            ctx.set_precision("f32")
+            for _ in range(2):
+                ctx.predict(KERNEL, dth, dx, dy, dxs, out=out_dev)
+            torch.cuda.synchronize()
+            ctx.set_profiling(True)
+            for kid in range(6):
+                ctx.profile_read(kid, reset=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            e0.record()
+            for _ in range(reps):
+                ctx.predict(KERNEL, dth, dx, dy, dxs, out=out_dev)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            var_ms, _ = ctx.profile_read(1)
+            fit_ms, _ = ctx.profile_read(0)
+            ctx.set_profiling(False)
+            ctx.set_precision("f64")
+            ex["fp32_mode"] = {"windows_per_s_per_gpu": B_PER_GPU / (ms * 1e-3), "ms_per_step": ms,
+                               "var_phase_ms": var_ms / reps, "fit_phase_ms": fit_ms / reps,
+                               "what": "cngp_config.precision = F32: FP64 factorisation + 3xTF32 mma.sync variance phase, "
+                                       "1e-4 normwise (tests/test_gpu_fp32_mode.py)"}
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        r = bc.mc(ctx, 1.0, rank, world)
+        if rank == 0:
+            ex["configs"]["configs[3]"] = r
+        r = bl.run(ctx, 32768, 2, rank, world)
+        if rank == 0:
+            ex["configs"]["configs[4]"] = r
+    except Exception as e:      # the headline must survive a failing extra leg
+        ex["error"] = repr(e)[:300]
+    return ex
 
 
 _RESULT_FD = None
@@ -395,10 +485,14 @@ def main():
         thr, _ = cpu_port_throughput(1, cores)
         per_core = int(max(1, min(64, round(12.0 * thr / cores))))
         v, dt = cpu_port_throughput(per_core, cores)
+        # the reference's own loop shape beside it: one predict call per test point (gp_slip_node.py:47-50)
+        vp, dtp = cpu_port_throughput(2, cores, worker=_cpu_worker_pointwise)
         emit({"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                          "sample": f"{per_core * cores} windows of the same workload in {dt:.1f} s "
-                                    f"(oracle/gp_oracle.py, vectorised {M_TEST}-RHS dtrtrs), {cores} processes x 1 BLAS "
-                                    f"thread"})
+              "sample": f"{per_core * cores} windows of the same workload in {dt:.1f} s "
+                        f"(oracle/gp_oracle.py, vectorised {M_TEST}-RHS dtrtrs), {cores} processes x 1 BLAS thread",
+              "faithful_loop": {"value": vp, "unit": UNIT,
+                                "sample": f"{2 * cores} windows in {dtp:.1f} s with the reference's per-point loop "
+                                          f"(one predict call per test point, gp_slip_node.py:47-50), same processes"}})
         return 0
     return run_ours(args)
 

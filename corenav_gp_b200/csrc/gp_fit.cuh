@@ -189,6 +189,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
   FastK<KID> fk;
   if (KID != KID_GENERIC && KID != KID_TILES) {
     fk.init(th);
+    fk.base = a.x[(long long)win * N];        // phase origin: the window's first stamp (gp_var_kernel uses the same)
     if (tid < 64) {
       const double t = EXP2_TAB64[tid];
       etab[tid] = fk.scale1() * t;

@@ -194,7 +194,10 @@ __global__ void __launch_bounds__(G * WG * 32, 1) gp_var_kernel(const VarArgs a)
     const int m = min(8 * m8 + r, M - 1);
     const double xm = a.xstar[(a.xstar_stride ? win * a.xstar_stride : 0) + m];
     PointFeat fm{xm, 0.0, 0.0, 0.0};
-    if (!TAB && KID != KID_GENERIC) fm = fk.point(xm);
+    if (!TAB && KID != KID_GENERIC) {
+      fk.base = a.feat[lw * (long long)(4 * n8)];      // the window's first training stamp, as in phase A
+      fm = fk.point(xm);
+    }
     const double* ktab = TAB ? a.ktab + lw * (long long)VAR_TAB_MAX : nullptr;
     const int* xip = TAB ? a.kxi + lw * (long long)n8 + 2 * q : nullptr;
     const int mi = TAB ? (int)(xm - km[1]) : 0;        // my test stamp as an offset from the window's base stamp

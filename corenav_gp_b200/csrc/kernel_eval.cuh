@@ -334,6 +334,11 @@ struct PointFeat {
 template <int KID>
 struct FastK {
   double c0, c1, c2, c3, c4;
+  // Phase origin of the periodic leaf's features.  The covariance only sees differences of phases, so any origin gives
+  // the same value in exact arithmetic; taking it at the window's first stamp keeps the phases O(span) - with the raw
+  // stamp at |x| ~ 1e6 the product x (2 pi / p) alone is rounded to 2e-11 rad, which costs 3e-8 on the predictive mean
+  // (GPy forms the difference x - x' first and does not have this problem).  x - base is exact for nearby stamps.
+  double base = 0.0;
   __device__ __forceinline__ void init(const double* th) {
     c0 = th[0];
     c1 = -0.5 / (th[1] * th[1]);
@@ -347,18 +352,19 @@ struct FastK {
   }
   __device__ __forceinline__ PointFeat point(double x) const {
     PointFeat f{x, __dmul_rn(x, x), 0.0, 0.0};
-    if (KID == KID_RBF_PER) sincos(x * c2, &f.s, &f.c);
+    if (KID == KID_RBF_PER) sincos((x - base) * c2, &f.s, &f.c);
     return f;
   }
   // GPy expanded-form r^2 from the features (same roundings as r2_expanded; -2 m is exact so the fma is too)
+  // ... and clipped at 0 as GPy does (np.clip(r2, 0, inf)): at |x| ~ 1e6 the expanded form is off by ~1e-4 in either
+  // direction, and a NEGATIVE r2 under a short length scale would give exp(+1e-4 / l^2) instead of 1 - far outside the
+  // 1e-9 parity (tests/test_gpu_parity_report.py::test_r2_clip_with_large_stamps).
   __device__ __forceinline__ double r2(const PointFeat& a, const PointFeat& b) const {
-    return fma(-2.0, __dmul_rn(a.x, b.x), __dadd_rn(a.xx, b.xx));
+    return fmax(fma(-2.0, __dmul_rn(a.x, b.x), __dadd_rn(a.xx, b.xx)), 0.0);
   }
   __device__ __forceinline__ double eval(const PointFeat& a, const PointFeat& b, bool same_sym) const {
     double rr = r2(a, b);
     if (same_sym) rr = 0.0;
-    // GPy clips r2 at 0; a negative r2 can only be rounding noise of the expanded form (|r2| < 1e-11 x^2), for which
-    // exp(r2 c1) differs from 1 by < 1e-13 - the clip is dropped here to keep two operations off the FP64 pipe.
     const double e1 = c0 * fast_exp(rr * c1);
     if (KID == KID_RBF) return e1;
     if (KID == KID_RBF_PER) {

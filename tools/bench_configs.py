@@ -177,8 +177,15 @@ def callback_fit(ctx):
         t0 = time.perf_counter()
         mean, sigma, status = ctx.gp_slip("rbf*brownian", t, s)
         dt = time.perf_counter() - t0
+        ctx.set_profiling(True)
+        for k in range(6):
+            ctx.profile_read(k, reset=True)
+        ctx.gp_slip("rbf*brownian", t, s)
+        prof = {name: ctx.profile_read(k) for k, name in ((0, "fit"), (1, "var"), (2, "grad"), (5, "misc"))}
+        ctx.set_profiling(False)
         out[f"B={B}"] = {"ms_per_call": dt * 1e3, "ms_per_window": dt * 1e3 / B, "ok": bool((status >= 0).all()),
-                         "m": int(mean.shape[1])}
+                         "m": int(mean.shape[1]),
+                         "kernel_ms_and_launches": {k: [round(v[0], 4), int(v[1])] for k, v in prof.items()}}
     return {"config": "node callback with hyper-parameter fit (rbf*brownian, n=149, horizon 600), host buffers", **out}
 
 

@@ -20,18 +20,11 @@ from corenav_gp_b200 import large, synthetic as syn  # noqa: E402
 from corenav_gp_b200.api import GpContext  # noqa: E402
 
 
-def main():
-    N = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
-    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-    lookahead = (sys.argv[3] != "0") if len(sys.argv) > 3 else True
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
+def run(ctx, N, reps, rank, world, lookahead=True):
+    """Factor one N-point window `reps` + 1 times (first one untimed) on `world` ranks; returns the result dict on every
+    rank (timings are the max over ranks)."""
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    ctx = GpContext(device=local)
     kname = "rbf+stdperiodic"
     th = np.array([0.01, 10.0, 0.0025, 37.0, 1.0, 1e-2])
     x, y = syn.slip_windows(5, 1, N)
@@ -57,12 +50,29 @@ def main():
     ctx.set_profiling(False)
     r = ctx.large_matvec(kname, th, win.x, out["alpha"].contiguous())
     res = float(torch.linalg.norm(r - win.y) / torch.linalg.norm(win.y))
+    best = min(times)
+    del win
+    return {"N": N, "n_gpus": world, "lookahead": lookahead, "ms": times, "best_ms": best,
+            "tflops_n3_over_3": N ** 3 / 3.0 / (best * 1e-3) * 1e-12, "lml": out["lml"],
+            "logdet": out["logdet"], "quad": out["quad"], "residual": res,
+            "rank0_kernel_ms_last_rep": prof_ms, "rank0_launches_last_rep": prof_n}
+
+
+def main():
+    N = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    lookahead = (sys.argv[3] != "0") if len(sys.argv) > 3 else True
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    ctx = GpContext(device=local)
+    line = run(ctx, N, reps, rank, world, lookahead)
     if rank == 0:
-        best = min(times)
-        print(json.dumps({"N": N, "n_gpus": world, "lookahead": lookahead, "ms": times, "best_ms": best,
-                          "tflops_n3_over_3": N ** 3 / 3.0 / (best * 1e-3) * 1e-12, "lml": out["lml"],
-                          "logdet": out["logdet"], "quad": out["quad"], "residual": res,
-                          "rank0_kernel_ms_last_rep": prof_ms, "rank0_launches_last_rep": prof_n}))
+        print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
