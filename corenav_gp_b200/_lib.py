@@ -69,6 +69,8 @@ SIGNATURES = {
                                         c_dp, c_ip, c_i32]),
     "cngp_optimize_batch": (C.c_int, [c_vp, C.POINTER(Kernel), c_dp, c_i64, c_dp, c_dp, c_i64, c_i32, c_i32, c_dp,
                                       c_dp, c_ip]),
+    "cngp_optimize_batch_mem": (C.c_int, [c_vp, C.POINTER(Kernel), c_dp, c_i64, c_dp, c_dp, c_i64, c_i32, c_i32, c_dp,
+                                          c_dp, c_ip, c_i32]),
     "cngp_gp_slip_batch": (C.c_int, [c_vp, C.POINTER(Kernel), c_dp, c_i64, c_dp, c_dp, c_i64, c_i32, c_i32, c_i32,
                                      c_dp, c_dp, c_ip, c_ip]),
     "cngp_default_stop_config": (None, [C.POINTER(StopConfig)]),

@@ -193,8 +193,25 @@ class GpContext:
         return lml, grad, status
 
     def optimize(self, kernel, x, y, theta0=None, max_iters: int = 1000):
-        """Batched m.optimize(): returns (theta [B,P], lml [B], iters [B]).  Host arrays only."""
+        """Batched m.optimize(): returns (theta [B,P], lml [B], iters [B]).  Host arrays, or CUDA tensors (then the
+        results are CUDA tensors too and the whole fit stays on the device)."""
         k = parse_kernel(kernel)
+        if _is_cuda(x):
+            B, N = x.shape
+            P = k.n_params + 1
+            th0 = torch.ones(P, dtype=torch.float64, device=x.device) if theta0 is None else theta0
+            stride = 0 if th0.dim() == 1 else P
+            theta = torch.empty((B, P), dtype=torch.float64, device=x.device)
+            lml = torch.empty(B, dtype=torch.float64, device=x.device)
+            iters = torch.empty(B, dtype=torch.int32, device=x.device)
+            a = [_Arg(th0, np.float64, True), _Arg(x, np.float64, True), _Arg(y, np.float64, True),
+                 _Arg(theta, np.float64, True, output=True), _Arg(lml, np.float64, True, output=True),
+                 _Arg(iters, np.int32, True, output=True)]
+            self._bind_stream(True)
+            rc = self.lib.cngp_optimize_batch_mem(self.h, C.byref(k), a[0].ptr, stride, a[1].ptr, a[2].ptr, B, N, max_iters,
+                                                  a[3].ptr, a[4].ptr, a[5].ptr, L.MEM_DEVICE)
+            self._check(rc, "cngp_optimize_batch_mem")
+            return theta, lml, iters
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.ascontiguousarray(y, dtype=np.float64)
         B, N = x.shape

@@ -677,7 +677,7 @@ extern "C" int cngp_predict_batch(cngp_ctx* ctx, const cngp_kernel* kernel, cons
 // ------------------------------------------------------------------------------------------------------------
 int cngp_lml_grad_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t C, const double* x,
                        const double* y, int64_t B, int32_t N, double* lml, double* grad, int32_t* status, int32_t mem,
-                       const int32_t* win_map) {
+                       const int32_t* win_map, const int32_t* skip) {
   if (!ctx) return CNGP_ERR_INVALID;
   if (!kernel || !theta || !x || !y || C < 0 || B < 0 || N <= 0) return fail(ctx, CNGP_ERR_INVALID, "lml_grad: bad argument");
   if (N > CNGP_MAX_N) return fail(ctx, CNGP_ERR_UNSUPPORTED, "lml_grad: N=%d > %d", N, CNGP_MAX_N);
@@ -706,7 +706,7 @@ int cngp_lml_grad_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* t
 
   const int nt = (N + 7) / 8;
   const size_t ltiles = (size_t)tiles_in_lower(nt) * 64;
-  const size_t per_problem = (ltiles * (grad ? 2 : 1) + (size_t)nt * 8 * 2) * sizeof(double);
+  const size_t per_problem = (ltiles * ((grad && nt > GRAD_SMEM_NT) ? 2 : 1) + (size_t)nt * 8 * 2) * sizeof(double);   // W only for the global variant
   if (ctx->scratch_bytes < per_problem)
     return fail(ctx, CNGP_ERR_NOMEM, "lml_grad: scratch_bytes = %zu cannot hold one problem (%zu bytes needed)",
                 ctx->scratch_bytes, per_problem);
@@ -715,12 +715,13 @@ int cngp_lml_grad_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* t
     const long long np = std::min<long long>(chunk, n_prob - p0);
     double* Lbuf = ctx->scratch;
     double* Wbuf = Lbuf + (size_t)np * ltiles;
-    double* zbuf = grad ? Wbuf + (size_t)np * ltiles : Wbuf;
+    double* zbuf = (grad && nt > GRAD_SMEM_NT) ? Wbuf + (size_t)np * ltiles : Wbuf;
     double* abuf = zbuf + (size_t)np * nt * 8;
     FitArgs fa;
     memset(&fa, 0, sizeof fa);
     fa.kp = kp;
     fa.lag_ok = (kprog_stationary(kp) && lag_tables_enabled()) ? 1 : 0;   // K(X,X) by integer lag when the stamps allow
+    fa.skip = skip;
     fa.theta = d_theta; fa.theta_stride = P; fa.theta_mode = d_map ? 3 : 2;
     fa.win_map = d_map;
     fa.x = d_x; fa.y = d_y; fa.N = N; fa.nt = nt; fa.n_windows = (int)B; fa.problem0 = p0;
@@ -737,8 +738,15 @@ int cngp_lml_grad_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* t
       ga.theta = d_theta; ga.theta_stride = P; ga.win_map = d_map;
       ga.x = d_x; ga.N = N; ga.nt = nt; ga.n_windows = (int)B; ga.problem0 = p0;
       ga.L = Lbuf; ga.W = Wbuf; ga.z = zbuf; ga.alpha = abuf; ga.status = d_status; ga.grad = d_grad;
+      ga.skip = skip;
       ctx->begin(CNGP_PROF_GRAD);
-      gp_grad_kernel<<<(unsigned)np, GRAD_THREADS, 0, ctx->stream>>>(ga);
+      if (nt <= GRAD_SMEM_NT) {
+        const size_t gsm = grad_smem_bytes(nt);
+        cudaFuncSetAttribute(gp_grad_kernel<GRAD_WARPS_SMEM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
+        gp_grad_kernel<GRAD_WARPS_SMEM, true><<<(unsigned)np, GRAD_WARPS_SMEM * 32, gsm, ctx->stream>>>(ga);
+      } else {
+        gp_grad_kernel<GRAD_WARPS_GLOBAL, false><<<(unsigned)np, GRAD_WARPS_GLOBAL * 32, 0, ctx->stream>>>(ga);
+      }
       ctx->end();
     }
     CU(ctx, cudaGetLastError());

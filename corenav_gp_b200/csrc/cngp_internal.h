@@ -10,7 +10,7 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
 // cngp_lml_grad_batch (win_map == nullptr) / cngp_lml_grad_windows (win_map given).
 int cngp_lml_grad_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t C, const double* x,
                        const double* y, int64_t B, int32_t N, double* lml, double* grad, int32_t* status, int32_t mem,
-                       const int32_t* win_map);
+                       const int32_t* win_map, const int32_t* skip = nullptr);   // skip[p] != 0: problem p is left untouched
 
 // error text of a context (cngp_api.cu)
 int cngp_set_error(cngp_ctx* ctx, int code, const char* text);

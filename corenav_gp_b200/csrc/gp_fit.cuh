@@ -79,6 +79,7 @@ struct FitArgs {
   double* ktab;          // [chunk][VAR_TAB_MAX]
   double* kmeta;         // [chunk][VAR_META]
   int* kxi;              // [chunk][nt*8]  training stamps as integer offsets from the base stamp
+  const int* skip;       // [n_problems] or null: problems with skip[p] != 0 are left untouched (finished optimiser windows)
   int f32_factor;        // FP32 mode: write the factor tiles split hi/lo TF32 (tile_store_split) for gp_var32_kernel
   int* n_lazy;           // += 1 for every window of the launch whose table is NOT valid (gp_var_kernel picks its path on it)
   // KID_TILES only (large-N blocked Cholesky, chol_large.cu): the SPD block is read from tile storage instead of being
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_ker
   const int r = lane >> 2, q = lane & 3;
   const long long lp = blockIdx.x;                 // problem within this launch
   const long long p = a.problem0 + lp;             // global problem
+  if (a.skip && a.skip[p]) return;
   const int win = a.win_map ? a.win_map[p] : (int)(p % a.n_windows);
   const long long ti = a.theta_mode == 0 ? 0 : (a.theta_mode == 1 ? (long long)win : (a.theta_mode == 3 ? p : p / a.n_windows));
   const double* th = a.theta + ti * a.theta_stride;

@@ -17,8 +17,10 @@
 
 namespace cngp {
 
-constexpr int GRAD_WARPS = 8;
-constexpr int GRAD_THREADS = GRAD_WARPS * 32;
+constexpr int GRAD_WARPS_GLOBAL = 8;    // factor tiles read from global memory / L2 (nt up to 32)
+constexpr int GRAD_WARPS_SMEM = 16;     // windows of up to GRAD_SMEM_NT row tiles: L and W live in shared memory
+constexpr int GRAD_SMEM_NT = 19;        // 2 x 190 tiles x 512 B = 190 KB (N <= 152: the reference's own windows, N = 134)
+constexpr size_t grad_smem_bytes(int nt) { return (size_t)nt * (nt + 1) * 512; }   // L + W: 2 x nt(nt+1)/2 tiles
 constexpr int GRAD_FAST_LEAVES = 4;   // leaves with register accumulators of their own (larger expressions: generic scan)
 
 struct GradArgs {
@@ -35,6 +37,7 @@ struct GradArgs {
   double* alpha;           // [chunk][nt*8] scratch / output
   const int* status;       // [n_problems]
   double* grad;            // [n_problems][P]
+  const int* skip;         // [n_problems] or null: problems with skip[p] != 0 are left untouched
 };
 
 // tile^T in the lane layout: lane (r,q) gets T[2q][r], T[2q+1][r]
@@ -43,7 +46,14 @@ __device__ __forceinline__ tile2 tile_load_T(const double* tile, int lane) {
   return tile2{tile[(2 * q) * 8 + r], tile[(2 * q + 1) * 8 + r]};
 }
 
-__global__ void __launch_bounds__(GRAD_THREADS) gp_grad_kernel(const GradArgs a) {
+// SMEM: the factor is copied into shared memory once and W = L^-1 is built there, so every operand of every tile product
+// is a shared-memory load - for one window (the node callback's m.optimize(): one CTA per evaluation) that removes the
+// L2 round trip from each dependent step, for a batch it removes the L2 traffic that bounds the global variant
+// (two 512-byte tile loads per tile product).
+template <int GRAD_WARPS, bool SMEM>
+__global__ void __launch_bounds__(GRAD_WARPS * 32) gp_grad_kernel(const GradArgs a) {
+  constexpr int GRAD_THREADS = GRAD_WARPS * 32;
+  extern __shared__ __align__(16) double gsm[];
   __shared__ double xs[CNGP_MAX_N + 8];
   __shared__ double al[CNGP_MAX_N + 8];
   __shared__ double zs[CNGP_MAX_N + 8];
@@ -56,12 +66,13 @@ __global__ void __launch_bounds__(GRAD_THREADS) gp_grad_kernel(const GradArgs a)
   const int r = lane >> 2, q = lane & 3;
   const long long lp = blockIdx.x;
   const long long p = a.problem0 + lp;
+  if (a.skip && a.skip[p]) return;
   const int win = a.win_map ? a.win_map[p] : (int)(p % a.n_windows);
   const long long cand = a.win_map ? p : p / a.n_windows;
   const double* th = a.theta + cand * a.theta_stride;
   const int N = a.N, nt = a.nt, P = a.kp.n_params + 1;
   const double* Lp = a.L + lp * (long long)tiles_in_lower(nt) * 64;
-  double* Wp = a.W + lp * (long long)tiles_in_lower(nt) * 64;
+  double* Wp = SMEM ? gsm + (size_t)tiles_in_lower(nt) * 64 : a.W + lp * (long long)tiles_in_lower(nt) * 64;
   const double* zp = a.z + lp * (long long)(nt * 8);
 
   for (int i = tid; i < nt * 8; i += GRAD_THREADS) {
@@ -75,6 +86,13 @@ __global__ void __launch_bounds__(GRAD_THREADS) gp_grad_kernel(const GradArgs a)
   if (a.status[p] < 0) {  // factorisation failed: NaN gradient
     if (tid < P) a.grad[p * P + tid] = __longlong_as_double(0x7ff8000000000000LL);
     return;
+  }
+  if (SMEM) {
+    const int nd = tiles_in_lower(nt) * 32;     // double2 elements of the factor
+    const double2* src = reinterpret_cast<const double2*>(Lp);
+    double2* dst = reinterpret_cast<double2*>(gsm);
+    for (int i = tid; i < nd; i += GRAD_THREADS) dst[i] = src[i];
+    Lp = gsm;
   }
   __syncthreads();
 

@@ -1,15 +1,16 @@
 // Host orchestration of the two entry points that sit directly behind the node callback
 // core_navigation/script/gp_slip_node.py:16-63:
 //
-//   cngp_optimize_batch   m.optimize() (gp_slip_node.py:36) for B windows at once.  GPy hands the objective to paramz'
+//   cngp_optimize_batch   m.optimize() (gp_slip_node.py:36) for B windows at once, entirely on the device.  GPy hands the objective to paramz'
 //                         "lbfgsb" optimiser = scipy.optimize.fmin_l_bfgs_b (L-BFGS-B 3.0, m = 10, factr = 1e7,
 //                         pgtol = 1e-5, maxfun = maxiter = 1000) on Logexp (softplus) transformed positives.  With no
 //                         bounds L-BFGS-B is L-BFGS with the More-Thuente line search (MINPACK-2 dcsrch/dcstep,
 //                         ftol 1e-3, gtol 0.9, xtol 0.1, first step 1/||g||, at most 20 trial points per search).  That
 //                         published algorithm is restated below as an explicit per-window state machine so that all B
 //                         optimisers advance in lock step: every round evaluates ONE trial point per still-active
-//                         window in a single batched GPU launch (cngp_lml_grad_windows).  Objective, gradient and
-//                         all O(N^3) work are on the GPU; the host only runs the O(m P) two-loop recursions.
+//                         window in a single batched GPU launch.  Objective, gradient AND the O(m P) two-loop recursions,
+//                         line searches and convergence tests run on the GPU (opt_feed_kernel); the host only
+//                         enqueues launches and reads one progress integer every few iterations.
 //   cngp_gp_slip_batch    the whole callback (rows a1-a7): 90 % train split, [optional fit], prediction grid
 //                         arange(min, max + horizon, 1), predict, keep [n:], sigma = 2 sqrt(var) (fused into the
 //                         variance kernel's epilogue).
@@ -27,87 +28,149 @@ using namespace cngp_host;
 
 namespace {
 
-// grow-only device buffers of the context (slots 30..36 belong to the optimiser): no cudaMalloc / cudaFree per call
-enum { SLOT_OPT_X = 30, SLOT_OPT_Y, SLOT_OPT_TH, SLOT_OPT_MAP, SLOT_OPT_LML, SLOT_OPT_GRAD, SLOT_OPT_ST };
+// grow-only device buffers of the context (slots 30..41 belong to the optimiser): no cudaMalloc / cudaFree per call
+enum { SLOT_OPT_X = 30, SLOT_OPT_Y, SLOT_OPT_TH, SLOT_OPT_MAP, SLOT_OPT_LML, SLOT_OPT_GRAD, SLOT_OPT_ST, SLOT_OPT_STATE,
+       SLOT_OPT_DONE, SLOT_OPT_NACT, SLOT_OPT_OUT, SLOT_OPT_TH0 };
 
 }  // namespace
 
-extern "C" int cngp_optimize_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta0, int64_t theta0_stride,
-                                   const double* x, const double* y, int64_t B, int32_t N, int32_t max_iters,
-                                   double* theta_out, double* lml_out, int32_t* iters_out) {
+// ---- device side of the optimiser: one L-BFGS-B state machine per window, advanced by a kernel ----
+namespace {
+
+__global__ void opt_init_kernel(Optimizer* st, const double* theta0, long long theta0_stride, int P, int max_iters,
+                                long long B, double* theta, int* win_map, int* done) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double ones[kMaxP];
+  for (int i = 0; i < P; ++i) ones[i] = 1.0;      // GPy initialises every hyper-parameter and the noise at 1.0
+  Optimizer& o = st[b];
+  o.init(theta0 ? theta0 + (theta0_stride ? b * theta0_stride : 0) : ones, P, max_iters);
+  for (int i = 0; i < P; ++i) theta[b * P + i] = softplus(o.zt[i]);
+  win_map[b] = (int)b;
+  done[b] = 0;
+}
+
+// Consume the objective / gradient evaluated at every still-active window's trial point and publish the next one.
+__global__ void opt_feed_kernel(Optimizer* st, const double* lml, const double* grad, const int* status, int P,
+                                long long B, double* theta, int* done, int* n_active) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || done[b]) return;
+  Optimizer& o = st[b];
+  double gz[kMaxP];
+  double fv;
+  if (status[b] < 0 || !isfinite(lml[b])) {   // not positive definite: a wall, as in the CPU path
+    fv = 1e300;
+    for (int i = 0; i < P; ++i) gz[i] = 0.0;
+  } else {
+    fv = -lml[b];
+    for (int i = 0; i < P; ++i) gz[i] = -grad[b * P + i] * softplus_gradfactor(theta[b * P + i]);
+  }
+  o.feed(fv, gz);
+  if (o.done) {
+    done[b] = 1;
+  } else {
+    for (int i = 0; i < P; ++i) theta[b * P + i] = softplus(o.zt[i]);
+    atomicAdd(n_active, 1);
+  }
+}
+
+__global__ void opt_result_kernel(const Optimizer* st, int P, long long B, double* theta_out, double* lml_out, int* iters_out) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const Optimizer& o = st[b];
+  for (int i = 0; i < P; ++i) theta_out[b * P + i] = softplus(o.z[i]);
+  if (lml_out) lml_out[b] = -o.f;
+  if (iters_out) iters_out[b] = o.nfev;
+}
+
+}  // namespace
+
+// m.optimize() for B windows.  Every L-BFGS-B state machine lives in device memory and is advanced by opt_feed_kernel;
+// one iteration is  gp_fit_kernel -> gp_grad_kernel -> opt_feed_kernel  on the context's stream with NO host round trip:
+// the host enqueues OPT_BLIND iterations at a time and only then reads one integer (windows still active).  Finished
+// windows are skipped by the kernels themselves (FitArgs::skip), so the tail of a batch costs empty launches, not work.
+int cngp_optimize_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta0, int64_t theta0_stride,
+                       const double* x, const double* y, int64_t B, int32_t N, int32_t max_iters, double* theta_out,
+                       double* lml_out, int32_t* iters_out, int32_t mem) {
   if (!ctx) return CNGP_ERR_INVALID;
   if (!kernel || !x || !y || !theta_out || B < 0 || N <= 0) return cngp_set_error(ctx, CNGP_ERR_INVALID, "optimize: bad argument");
   if (B == 0) return CNGP_OK;
   cngp_kernel kk = *kernel;
   if (cngp_kernel_finalize(&kk) != CNGP_OK) return cngp_set_error(ctx, CNGP_ERR_INVALID, "optimize: invalid kernel expression");
   const int P = kk.n_params + 1;
+  if (P > kMaxP) return cngp_set_error(ctx, CNGP_ERR_UNSUPPORTED, "optimize: too many hyper-parameters");
   if (max_iters <= 0) max_iters = 1000;
+  const bool host = mem == CNGP_MEM_HOST;
 
-  std::vector<Optimizer> opt((size_t)B);
-  std::vector<double> ones((size_t)P, 1.0);   // GPy initialises every hyper-parameter and the noise at 1.0
-  for (int64_t b = 0; b < B; ++b)
-    opt[b].init(theta0 ? theta0 + (theta0_stride ? b * theta0_stride : 0) : ones.data(), P, max_iters);
-
-  // Everything below is ordered on the context's stream on the context's device: the uploads are cudaMemcpyAsync on
-  // that stream (the kernels run there, and it is a non-blocking stream, so legacy-stream copies would not order them).
+  // Everything below is ordered on the context's stream on the context's device.
   if (cudaSetDevice(cngp_ctx_device(ctx)) != cudaSuccess) return cngp_set_error(ctx, CNGP_ERR_CUDA, "optimize: cudaSetDevice failed");
   cudaStream_t s = cngp_ctx_stream(ctx);
-  struct { void* p; } dx, dy, dth, dmap, dlml, dgrad, dst;
   const size_t xy = sizeof(double) * (size_t)B * N;
-  dx.p = cngp_ctx_buf(ctx, SLOT_OPT_X, xy);
-  dy.p = cngp_ctx_buf(ctx, SLOT_OPT_Y, xy);
-  dth.p = cngp_ctx_buf(ctx, SLOT_OPT_TH, sizeof(double) * B * P);
-  dmap.p = cngp_ctx_buf(ctx, SLOT_OPT_MAP, sizeof(int) * B);
-  dlml.p = cngp_ctx_buf(ctx, SLOT_OPT_LML, sizeof(double) * B);
-  dgrad.p = cngp_ctx_buf(ctx, SLOT_OPT_GRAD, sizeof(double) * B * P);
-  dst.p = cngp_ctx_buf(ctx, SLOT_OPT_ST, sizeof(int) * B);
-  if (!dx.p || !dy.p || !dth.p || !dmap.p || !dlml.p || !dgrad.p || !dst.p)
+  Optimizer* d_st = (Optimizer*)cngp_ctx_buf(ctx, SLOT_OPT_STATE, sizeof(Optimizer) * (size_t)B);
+  double* d_th = (double*)cngp_ctx_buf(ctx, SLOT_OPT_TH, sizeof(double) * B * P);
+  int* d_map = (int*)cngp_ctx_buf(ctx, SLOT_OPT_MAP, sizeof(int) * B);
+  double* d_lml = (double*)cngp_ctx_buf(ctx, SLOT_OPT_LML, sizeof(double) * B);
+  double* d_grad = (double*)cngp_ctx_buf(ctx, SLOT_OPT_GRAD, sizeof(double) * B * P);
+  int* d_st_fit = (int*)cngp_ctx_buf(ctx, SLOT_OPT_ST, sizeof(int) * B);
+  int* d_done = (int*)cngp_ctx_buf(ctx, SLOT_OPT_DONE, sizeof(int) * B);
+  int* d_nact = (int*)cngp_ctx_buf(ctx, SLOT_OPT_NACT, 64);
+  if (!d_st || !d_th || !d_map || !d_lml || !d_grad || !d_st_fit || !d_done || !d_nact)
     return cngp_set_error(ctx, CNGP_ERR_NOMEM, "optimize: device allocation failed");
-  if (cudaMemcpyAsync(dx.p, x, xy, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-      cudaMemcpyAsync(dy.p, y, xy, cudaMemcpyHostToDevice, s) != cudaSuccess)
-    return cngp_set_error(ctx, CNGP_ERR_CUDA, "optimize: upload failed");
-
-  std::vector<int> active;
-  std::vector<double> th((size_t)B * P), lml((size_t)B), grad((size_t)B * P), gz((size_t)P);
-  std::vector<int> status((size_t)B);
-  for (;;) {
-    active.clear();
-    for (int64_t b = 0; b < B; ++b)
-      if (!opt[b].done) active.push_back((int)b);
-    if (active.empty()) break;
-    const size_t na = active.size();
-    for (size_t a = 0; a < na; ++a)
-      for (int i = 0; i < P; ++i) th[a * P + i] = softplus(opt[active[a]].zt[i]);
-    if (cudaMemcpyAsync(dth.p, th.data(), sizeof(double) * na * P, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-        cudaMemcpyAsync(dmap.p, active.data(), sizeof(int) * na, cudaMemcpyHostToDevice, s) != cudaSuccess)
+  const double *d_x = x, *d_y = y, *d_th0 = theta0;
+  double* d_out = theta_out; double* d_lout = lml_out; int* d_iout = iters_out;
+  if (host) {
+    double* bx = (double*)cngp_ctx_buf(ctx, SLOT_OPT_X, xy);
+    double* by = (double*)cngp_ctx_buf(ctx, SLOT_OPT_Y, xy);
+    double* bo = (double*)cngp_ctx_buf(ctx, SLOT_OPT_OUT, sizeof(double) * B * (P + 1) + sizeof(int) * B);
+    double* b0 = theta0 ? (double*)cngp_ctx_buf(ctx, SLOT_OPT_TH0, sizeof(double) * (theta0_stride ? B * theta0_stride : P)) : nullptr;
+    if (!bx || !by || !bo || (theta0 && !b0)) return cngp_set_error(ctx, CNGP_ERR_NOMEM, "optimize: device allocation failed");
+    if (cudaMemcpyAsync(bx, x, xy, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(by, y, xy, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        (theta0 && cudaMemcpyAsync(b0, theta0, sizeof(double) * (theta0_stride ? B * theta0_stride : P),
+                                   cudaMemcpyHostToDevice, s) != cudaSuccess))
       return cngp_set_error(ctx, CNGP_ERR_CUDA, "optimize: upload failed");
-    int rc = cngp_lml_grad_impl(ctx, &kk, (const double*)dth.p, (int64_t)na, (const double*)dx.p, (const double*)dy.p, B, N,
-                                (double*)dlml.p, (double*)dgrad.p, (int*)dst.p, CNGP_MEM_DEVICE, (const int*)dmap.p);
-    if (rc) return rc;
-    if (cudaMemcpyAsync(lml.data(), dlml.p, sizeof(double) * na, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaMemcpyAsync(grad.data(), dgrad.p, sizeof(double) * na * P, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaMemcpyAsync(status.data(), dst.p, sizeof(int) * na, cudaMemcpyDeviceToHost, s) != cudaSuccess)
-      return cngp_set_error(ctx, CNGP_ERR_CUDA, "optimize: download failed");
-    if ((rc = cngp_sync(ctx))) return rc;     // the host state machines need the values; th / active are re-written next
-    for (size_t a = 0; a < na; ++a) {
-      Optimizer& o = opt[active[a]];
-      double fv;
-      if (status[a] < 0 || !std::isfinite(lml[a])) {   // not positive definite: a wall, as in the CPU path
-        fv = 1e300;
-        for (int i = 0; i < P; ++i) gz[i] = 0.0;
-      } else {
-        fv = -lml[a];
-        for (int i = 0; i < P; ++i) gz[i] = -grad[a * P + i] * softplus_gradfactor(th[a * P + i]);
-      }
-      o.feed(fv, gz.data());
-    }
+    d_x = bx; d_y = by; d_th0 = b0;
+    d_out = bo; d_lout = bo + (size_t)B * P; d_iout = (int*)(bo + (size_t)B * (P + 1));
   }
-  for (int64_t b = 0; b < B; ++b) {
-    for (int i = 0; i < P; ++i) theta_out[b * P + i] = softplus(opt[b].z[i]);
-    if (lml_out) lml_out[b] = -opt[b].f;
-    if (iters_out) iters_out[b] = opt[b].nfev;
+  const unsigned blocks = (unsigned)((B + 63) / 64);
+  opt_init_kernel<<<blocks, 64, 0, s>>>(d_st, d_th0, theta0_stride, P, max_iters, B, d_th, d_map, d_done);
+  constexpr int OPT_BLIND = 6;
+  int n_active = 1;
+  for (int round = 0; n_active > 0 && round * OPT_BLIND <= max_iters + OPT_BLIND; ++round) {
+    for (int k = 0; k < OPT_BLIND; ++k) {
+      if (cudaMemsetAsync(d_nact, 0, sizeof(int), s) != cudaSuccess) return cngp_set_error(ctx, CNGP_ERR_CUDA, "optimize: memset failed");
+      const int rc = cngp_lml_grad_impl(ctx, &kk, d_th, B, d_x, d_y, B, N, d_lml, d_grad, d_st_fit, CNGP_MEM_DEVICE, d_map, d_done);
+      if (rc) return rc;
+      opt_feed_kernel<<<blocks, 64, 0, s>>>(d_st, d_lml, d_grad, d_st_fit, P, B, d_th, d_done, d_nact);
+    }
+    if (cudaMemcpyAsync(&n_active, d_nact, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+      return cngp_set_error(ctx, CNGP_ERR_CUDA, "optimize: progress read failed");
+  }
+  opt_result_kernel<<<blocks, 64, 0, s>>>(d_st, P, B, d_out, d_lout, d_iout);
+  if (cudaGetLastError() != cudaSuccess) return cngp_set_error(ctx, CNGP_ERR_CUDA, "optimize: kernel launch failed");
+  if (host) {
+    if (cudaMemcpyAsync(theta_out, d_out, sizeof(double) * B * P, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        (lml_out && cudaMemcpyAsync(lml_out, d_lout, sizeof(double) * B, cudaMemcpyDeviceToHost, s) != cudaSuccess) ||
+        (iters_out && cudaMemcpyAsync(iters_out, d_iout, sizeof(int) * B, cudaMemcpyDeviceToHost, s) != cudaSuccess) ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+      return cngp_set_error(ctx, CNGP_ERR_CUDA, "optimize: download failed");
   }
   return CNGP_OK;
+}
+
+extern "C" int cngp_optimize_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta0, int64_t theta0_stride,
+                                   const double* x, const double* y, int64_t B, int32_t N, int32_t max_iters,
+                                   double* theta_out, double* lml_out, int32_t* iters_out) {
+  return cngp_optimize_impl(ctx, kernel, theta0, theta0_stride, x, y, B, N, max_iters, theta_out, lml_out, iters_out,
+                            CNGP_MEM_HOST);
+}
+
+extern "C" int cngp_optimize_batch_mem(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta0,
+                                       int64_t theta0_stride, const double* x, const double* y, int64_t B, int32_t N,
+                                       int32_t max_iters, double* theta_out, double* lml_out, int32_t* iters_out,
+                                       int32_t mem) {
+  return cngp_optimize_impl(ctx, kernel, theta0, theta0_stride, x, y, B, N, max_iters, theta_out, lml_out, iters_out, mem);
 }
 
 extern "C" int cngp_gp_slip_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t theta_stride,

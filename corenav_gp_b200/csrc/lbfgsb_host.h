@@ -1,11 +1,21 @@
-// Host-side L-BFGS-B (no bounds) as a resumable per-window state machine; see gp_slip.cu for what it restates.
-// Pure C++ (no CUDA): included by gp_slip.cu and by the CPU test shim tests/host/lbfgsb_shim.cpp.
+// L-BFGS-B (no bounds) as a resumable per-window state machine; see gp_slip.cu for what it restates.
+// Plain C++ with fixed-size state and no library containers, usable on the host AND in device code: gp_slip.cu runs one
+// state machine per window in a device kernel (opt_feed_kernel - no host round trip per iteration), the CPU test shim
+// tests/host/lbfgsb_shim.cpp drives the very same code with a caller-supplied objective.
 #pragma once
-#include <algorithm>
 #include <cmath>
-#include <vector>
+
+#ifdef __CUDACC__
+#define CNGP_HD __host__ __device__
+#else
+#define CNGP_HD
+#endif
 
 namespace cngp_host {
+
+constexpr int kMaxP = 25;                         // CNGP_MAX_PARAMS + 1 (kernel hyper-parameters + noise)
+CNGP_HD inline double hd_max(double a, double b) { return a > b ? a : b; }
+CNGP_HD inline double hd_min(double a, double b) { return a < b ? a : b; }
 
 constexpr double kEps = 2.220446049250313e-16;   // dpmeps
 constexpr double kFactr = 1e7, kPgtol = 1e-5;    // scipy fmin_l_bfgs_b defaults (paramz passes none)
@@ -13,18 +23,18 @@ constexpr int kHist = 10;                         // m
 constexpr double kFtol = 1e-3, kGtol = 0.9, kXtol = 0.1, kStpMax = 1e10;
 constexpr double kLim = 36.0;                     // paramz transformations._lim_val
 
-inline double softplus(double z) { return z > kLim ? z : log1p(exp(z)); }
-inline double softplus_inv(double t) { return t > kLim ? t : log(expm1(t)); }
-inline double softplus_gradfactor(double t) { return t > kLim ? 1.0 : -expm1(-t); }
+CNGP_HD inline double softplus(double z) { return z > kLim ? z : log1p(exp(z)); }
+CNGP_HD inline double softplus_inv(double t) { return t > kLim ? t : log(expm1(t)); }
+CNGP_HD inline double softplus_gradfactor(double t) { return t > kLim ? 1.0 : -expm1(-t); }
 
 // MINPACK-2 dcstep: safeguarded cubic/quadratic step of the More-Thuente search.
-void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy, double& stp, double fp, double dp,
+CNGP_HD inline void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy, double& stp, double fp, double dp,
             bool& brackt, double stpmin, double stpmax) {
   const double sgnd = dp * (dx / fabs(dx));
   double stpf, stpc, stpq, theta, s, gamma, p, q, r;
   if (fp > fx) {                       // case 1: higher function value - the minimum is bracketed
     theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    s = std::max(fabs(theta), std::max(fabs(dx), fabs(dp)));
+    s = hd_max(fabs(theta), hd_max(fabs(dx), fabs(dp)));
     gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
     if (stp < stx) gamma = -gamma;
     p = (gamma - dx) + theta;
@@ -36,7 +46,7 @@ void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double
     brackt = true;
   } else if (sgnd < 0.0) {             // case 2: lower value, derivatives of opposite sign - bracketed
     theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    s = std::max(fabs(theta), std::max(fabs(dx), fabs(dp)));
+    s = hd_max(fabs(theta), hd_max(fabs(dx), fabs(dp)));
     gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
     if (stp > stx) gamma = -gamma;
     p = (gamma - dp) + theta;
@@ -48,8 +58,8 @@ void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double
     brackt = true;
   } else if (fabs(dp) < fabs(dx)) {    // case 3: lower value, same sign, derivative magnitude decreases
     theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    s = std::max(fabs(theta), std::max(fabs(dx), fabs(dp)));
-    gamma = s * sqrt(std::max(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
+    s = hd_max(fabs(theta), hd_max(fabs(dx), fabs(dp)));
+    gamma = s * sqrt(hd_max(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
     if (stp > stx) gamma = -gamma;
     p = (gamma - dp) + theta;
     q = (gamma + (dx - dp)) + gamma;
@@ -59,16 +69,16 @@ void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double
     stpq = stp + (dp / (dp - dx)) * (stx - stp);
     if (brackt) {
       stpf = fabs(stpc - stp) < fabs(stpq - stp) ? stpc : stpq;
-      stpf = stp > stx ? std::min(stp + 0.66 * (sty - stp), stpf) : std::max(stp + 0.66 * (sty - stp), stpf);
+      stpf = stp > stx ? hd_min(stp + 0.66 * (sty - stp), stpf) : hd_max(stp + 0.66 * (sty - stp), stpf);
     } else {
       stpf = fabs(stpc - stp) > fabs(stpq - stp) ? stpc : stpq;
-      stpf = std::min(stpmax, stpf);
-      stpf = std::max(stpmin, stpf);
+      stpf = hd_min(stpmax, stpf);
+      stpf = hd_max(stpmin, stpf);
     }
   } else {                             // case 4: lower value, same sign, derivative does not decrease
     if (brackt) {
       theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
-      s = std::max(fabs(theta), std::max(fabs(dy), fabs(dp)));
+      s = hd_max(fabs(theta), hd_max(fabs(dy), fabs(dp)));
       gamma = s * sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
       if (stp > sty) gamma = -gamma;
       p = (gamma - dp) + theta;
@@ -94,13 +104,13 @@ struct LineSearch {
   bool brackt;
   int stage;
   double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1, stp;
-  void start(double f0, double g0, double stp0) {
+  CNGP_HD void start(double f0, double g0, double stp0) {
     brackt = false; stage = 1; finit = f0; ginit = g0; gtest = kFtol * ginit;
     width = kStpMax; width1 = 2.0 * width;
     stx = 0.0; fx = finit; gx = ginit; sty = 0.0; fy = finit; gy = ginit;
     stmin = 0.0; stp = stp0; stmax = stp + 4.0 * stp;
   }
-  bool step(double f, double g) {
+  CNGP_HD bool step(double f, double g) {
     const double ftest = finit + stp * gtest;
     if (stage == 1 && f <= ftest && g >= 0.0) stage = 2;
     if (brackt && (stp <= stmin || stp >= stmax)) return true;          // rounding errors prevent progress
@@ -122,12 +132,12 @@ struct LineSearch {
       width = fabs(sty - stx);
     }
     if (brackt) {
-      stmin = std::min(stx, sty); stmax = std::max(stx, sty);
+      stmin = hd_min(stx, sty); stmax = hd_max(stx, sty);
     } else {
       stmin = stp + 1.1 * (stp - stx); stmax = stp + 4.0 * (stp - stx);
     }
-    stp = std::max(stp, 0.0);
-    stp = std::min(stp, kStpMax);
+    stp = hd_max(stp, 0.0);
+    stp = hd_min(stp, kStpMax);
     if ((brackt && (stp <= stmin || stp >= stmax)) || (brackt && stmax - stmin <= kXtol * stmax)) stp = stx;
     return false;
   }
@@ -136,53 +146,58 @@ struct LineSearch {
 // One window's L-BFGS-B (no bounds) run, driven from outside: trial() is the point to evaluate next, feed(f, g)
 // consumes the objective and gradient there.
 struct Optimizer {
-  int P = 0, max_iters = 1000;
-  std::vector<double> z, g, d, zt, s_hist, y_hist, rho;
-  double f = 0.0, gd0 = 0.0, dnorm = 0.0;
-  int hist_n = 0, hist_head = 0, iters = 0, nfev = 0, ls_evals = 0;
-  bool done = false, first = true;
+  int P, max_iters;
+  double z[kMaxP], g[kMaxP], d[kMaxP], zt[kMaxP], s_hist[kHist * kMaxP], y_hist[kHist * kMaxP], rho[kHist];
+  double f, gd0, dnorm;
+  int hist_n, hist_head, iters, nfev, ls_evals;
+  bool done, first;
   LineSearch ls;
 
-  void init(const double* theta0, int P_, int max_iters_) {
+  CNGP_HD void init(const double* theta0, int P_, int max_iters_) {
     P = P_; max_iters = max_iters_;
-    z.resize(P); g.resize(P); d.resize(P); zt.resize(P);
-    s_hist.assign((size_t)kHist * P, 0.0); y_hist.assign((size_t)kHist * P, 0.0); rho.assign(kHist, 0.0);
+    f = gd0 = dnorm = 0.0;
+    hist_n = hist_head = iters = nfev = ls_evals = 0;
+    done = false; first = true;
+    for (int i = 0; i < kHist * kMaxP; ++i) s_hist[i] = y_hist[i] = 0.0;
+    for (int i = 0; i < kHist; ++i) rho[i] = 0.0;
+    for (int i = 0; i < kMaxP; ++i) z[i] = g[i] = d[i] = zt[i] = 0.0;
     for (int i = 0; i < P; ++i) zt[i] = z[i] = softplus_inv(theta0[i]);
   }
-  double gmax(const std::vector<double>& v) const {
+  CNGP_HD double gmax(const double* v) const {
     double m = 0.0;
-    for (double e : v) m = std::max(m, fabs(e));
+    for (int i = 0; i < P; ++i) m = hd_max(m, fabs(v[i]));
     return m;
   }
   // d = -H g by the two-loop recursion (H0 = s'y / y'y of the newest pair)
-  void direction() {
-    std::vector<double> qv(g), al(kHist);
+  CNGP_HD void direction() {
+    double qv[kMaxP], al[kHist];
+    for (int i = 0; i < P; ++i) qv[i] = g[i];
     for (int t = 0; t < hist_n; ++t) {
       const int k = (hist_head - 1 - t + 2 * kHist) % kHist;
       double a = 0.0;
-      for (int i = 0; i < P; ++i) a += s_hist[(size_t)k * P + i] * qv[i];
+      for (int i = 0; i < P; ++i) a += s_hist[k * P + i] * qv[i];
       a *= rho[k];
       al[k] = a;
-      for (int i = 0; i < P; ++i) qv[i] -= a * y_hist[(size_t)k * P + i];
+      for (int i = 0; i < P; ++i) qv[i] -= a * y_hist[k * P + i];
     }
     if (hist_n > 0) {
       const int k = (hist_head - 1 + kHist) % kHist;
       double yy = 0.0;
-      for (int i = 0; i < P; ++i) yy += y_hist[(size_t)k * P + i] * y_hist[(size_t)k * P + i];
+      for (int i = 0; i < P; ++i) yy += y_hist[k * P + i] * y_hist[k * P + i];
       const double gam = 1.0 / (rho[k] * yy);
       for (int i = 0; i < P; ++i) qv[i] *= gam;
     }
     for (int t = hist_n - 1; t >= 0; --t) {
       const int k = (hist_head - 1 - t + 2 * kHist) % kHist;
       double b = 0.0;
-      for (int i = 0; i < P; ++i) b += y_hist[(size_t)k * P + i] * qv[i];
+      for (int i = 0; i < P; ++i) b += y_hist[k * P + i] * qv[i];
       b *= rho[k];
-      for (int i = 0; i < P; ++i) qv[i] += (al[k] - b) * s_hist[(size_t)k * P + i];
+      for (int i = 0; i < P; ++i) qv[i] += (al[k] - b) * s_hist[k * P + i];
     }
     for (int i = 0; i < P; ++i) d[i] = -qv[i];
   }
   // set up the line search from the current iterate; returns false when no descent direction can be found
-  bool begin_search() {
+  CNGP_HD bool begin_search() {
     for (int attempt = 0; attempt < 2; ++attempt) {
       direction();
       gd0 = 0.0; dnorm = 0.0;
@@ -192,13 +207,13 @@ struct Optimizer {
       if (hist_n == 0) return false;          // steepest descent is not a descent direction: g == 0
       hist_n = 0;                             // refresh the memory and retry (lnsrlb info = -4)
     }
-    const double stp0 = (iters == 0) ? std::min(1.0 / dnorm, kStpMax) : 1.0;
+    const double stp0 = (iters == 0) ? hd_min(1.0 / dnorm, kStpMax) : 1.0;
     ls.start(f, gd0, stp0);
     ls_evals = 0;
     for (int i = 0; i < P; ++i) zt[i] = z[i] + ls.stp * d[i];
     return true;
   }
-  void feed(double ft, const double* gt) {
+  CNGP_HD void feed(double ft, const double* gt) {
     ++nfev;
     if (first) {
       first = false;
@@ -229,18 +244,18 @@ struct Optimizer {
     if (dr > kEps * ddum) {
       const int k = hist_head;
       for (int i = 0; i < P; ++i) {
-        s_hist[(size_t)k * P + i] = stp_eval * d[i];
-        y_hist[(size_t)k * P + i] = gt[i] - g[i];
+        s_hist[k * P + i] = stp_eval * d[i];
+        y_hist[k * P + i] = gt[i] - g[i];
       }
       rho[k] = 1.0 / dr;
       hist_head = (hist_head + 1) % kHist;
-      hist_n = std::min(hist_n + 1, kHist);
+      hist_n = hd_min(hist_n + 1, kHist);
     }
     for (int i = 0; i < P; ++i) { z[i] += stp_eval * d[i]; g[i] = gt[i]; }
     f = ft;
     ++iters;
     if (gmax(g) <= kPgtol) { done = true; return; }
-    if (fold - f <= kEps * kFactr * std::max(std::max(fabs(fold), fabs(f)), 1.0)) { done = true; return; }
+    if (fold - f <= kEps * kFactr * hd_max(hd_max(fabs(fold), fabs(f)), 1.0)) { done = true; return; }
     if (iters >= max_iters || nfev >= max_iters) { done = true; return; }
     if (!begin_search()) done = true;
   }

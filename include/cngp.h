@@ -159,6 +159,11 @@ int cngp_lml_grad_windows(cngp_ctx* ctx, const cngp_kernel* kernel, const double
 int cngp_optimize_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta0, int64_t theta0_stride,
                         const double* x, const double* y, int64_t B, int32_t N, int32_t max_iters,
                         double* theta_out, double* lml_out, int32_t* iters_out);
+/* The same with the array arguments in device memory when mem = CNGP_MEM_DEVICE (stream-ordered, returns after the
+ * optimisers have finished; results are left in the device buffers). */
+int cngp_optimize_batch_mem(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta0, int64_t theta0_stride,
+                        const double* x, const double* y, int64_t B, int32_t N, int32_t max_iters,
+                        double* theta_out, double* lml_out, int32_t* iters_out, int32_t mem);
 
 /* The node callback for B windows of n samples each (rows a1-a7): train on the first int(0.9 n) samples, predict on
  * arange(min(time), max(time) + horizon, 1), keep entries [n:], sigma = 2 sqrt(var).  m_out = number of kept points

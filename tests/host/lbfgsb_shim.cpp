@@ -1,5 +1,7 @@
 // CPU test shim: drives the product's L-BFGS-B state machine (corenav_gp_b200/csrc/lbfgsb_host.h) with a caller-supplied
 // objective, exactly as cngp_optimize_batch drives it with the GPU objective.  Built by tests/test_host_lbfgsb.py.
+#include <vector>
+
 #include "../../corenav_gp_b200/csrc/lbfgsb_host.h"
 
 extern "C" int lbfgsb_shim_minimize(int P, const double* theta0, int max_iters,

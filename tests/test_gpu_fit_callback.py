@@ -128,3 +128,23 @@ def test_python_node_mirror(slipval):
     mu, sg = go.gp_slip_callback(t, s, go.KernelExpr("rbf*brownian"), theta=th[:-1], noise=th[-1])
     assert got and got[0] is msg and node.pub.last is msg
     assert rel(msg.mean, mu) < TOL and rel(msg.sigma, sg) < TOL
+
+
+def test_optimize_on_device_buffers_matches_host_call(gp_ctx):
+    """cngp_optimize_batch_mem with CUDA tensors: the whole fit (objective, gradient, L-BFGS-B state machines) stays on
+    the device; same optima as the host-buffer call, finished windows are skipped while the others still iterate."""
+    import torch
+    B, N = 37, 64
+    x, y = syn.slip_windows(300, B, N)
+    th_h, lml_h, it_h = gp_ctx.optimize("rbf", x, y)
+    th_d, lml_d, it_d = gp_ctx.optimize("rbf", torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(th_h, th_d.cpu().numpy()) and np.array_equal(lml_h, lml_d.cpu().numpy())
+    assert np.array_equal(it_h, it_d.cpu().numpy())
+    assert it_h.min() < it_h.max(), "windows should need different numbers of evaluations"
+    e = go.KernelExpr("rbf")
+    for b in (0, 11, 36):
+        inf = go.inference(e, th_h[b, :-1], th_h[b, -1], x[b], y[b], want_grad=True)
+        assert rel(lml_h[b], inf.lml) < TOL                       # the reported LML is the LML at the returned theta
+        _, _, lml_ref, _ = go.optimize(e, x[b], y[b])
+        assert lml_h[b] >= lml_ref - 1e-6 * abs(lml_ref)

@@ -166,7 +166,7 @@ def callback_fit(ctx):
     """Rows a1-a7 end to end, as the reference runs them: the node callback with the hyper-parameter fit (L-BFGS-B from
     all-ones on softplus parameters, gp_slip_node.py:31-36), n = 149 samples (134 training points), 600-step horizon."""
     out = {}
-    for B in (1, 64):
+    for B in (1, 64, 4096):
         rows = []
         for b in range(B):
             t = 21.0 + np.arange(149)
@@ -183,7 +183,8 @@ def callback_fit(ctx):
         ctx.gp_slip("rbf*brownian", t, s)
         prof = {name: ctx.profile_read(k) for k, name in ((0, "fit"), (1, "var"), (2, "grad"), (5, "misc"))}
         ctx.set_profiling(False)
-        out[f"B={B}"] = {"ms_per_call": dt * 1e3, "ms_per_window": dt * 1e3 / B, "ok": bool((status >= 0).all()),
+        out[f"B={B}"] = {"ms_per_call": dt * 1e3, "ms_per_window": dt * 1e3 / B, "windows_per_s": B / dt,
+                         "ok": bool((status >= 0).all()),
                          "m": int(mean.shape[1]),
                          "kernel_ms_and_launches": {k: [round(v[0], 4), int(v[1])] for k, v in prof.items()}}
     return {"config": "node callback with hyper-parameter fit (rbf*brownian, n=149, horizon 600), host buffers", **out}
