@@ -268,9 +268,12 @@ class GpContext:
                 setattr(c, key, v)
         return c
 
-    def zupt_lookahead(self, mean, sigma, P, Q, STM, Hvec, pos, cfg: Optional[L.StopConfig] = None):
+    def zupt_lookahead(self, mean, sigma, P, Q, STM, Hvec, pos, cfg: Optional[L.StopConfig] = None,
+                       want_state: bool = False):
         """Batched GpPredictor look-ahead.  mean, sigma [B,M]; each of P,Q,STM ([225] or [B,225]), Hvec ([60] or
-        [B,60]), pos ([3] or [B,3]) is shared or per window.  Returns dict(triggered, i_stop, step_stop, xy_err)."""
+        [B,60]), pos ([3] or [B,3]) is shared or per window.  Returns dict(triggered, i_stop, step_stop, xy_err);
+        want_state adds P_final [B,225], K_final [B,60], R_final [B,16] - what the reference leaves in the public
+        members P_pred, K_pred, R_IP after the callback (gp_predictor.h:36-43)."""
         dev = _is_cuda(mean)
         B, M = mean.shape
         cfg = cfg or self.stop_config()
@@ -291,6 +294,16 @@ class GpContext:
         a = [_Arg(mean, np.float64, dev), _Arg(sigma, np.float64, dev), _Arg(trig, np.int32, dev),
              _Arg(i_stop, np.int32, dev), _Arg(step, np.int32, dev), _Arg(xy, np.float64, dev)]
         self._bind_stream(dev)
+        if want_state:
+            Pf, Kf, Rf = (self._empty((B, n), np.float64, dev) for n in (225, 60, 16))
+            s3 = [_Arg(Pf, np.float64, dev, output=True), _Arg(Kf, np.float64, dev, output=True),
+                  _Arg(Rf, np.float64, dev, output=True)]
+            rc = self.lib.cngp_zupt_lookahead_batch_ex(self.h, a[0].ptr, a[1].ptr, B, M, *[c.ptr for c in ctx_args], mask,
+                                                       C.byref(cfg), a[2].ptr, a[3].ptr, a[4].ptr, a[5].ptr,
+                                                       s3[0].ptr, s3[1].ptr, s3[2].ptr,
+                                                       L.MEM_DEVICE if dev else L.MEM_HOST)
+            self._check(rc, "cngp_zupt_lookahead_batch_ex")
+            return dict(triggered=trig, i_stop=i_stop, step_stop=step, xy_err=xy, P_final=Pf, K_final=Kf, R_final=Rf)
         rc = self.lib.cngp_zupt_lookahead_batch(self.h, a[0].ptr, a[1].ptr, B, M, *[c.ptr for c in ctx_args], mask,
                                                 C.byref(cfg), a[2].ptr, a[3].ptr, a[4].ptr, a[5].ptr,
                                                 L.MEM_DEVICE if dev else L.MEM_HOST)

@@ -20,7 +20,7 @@
 
 extern "C" int cngp_launch_lookahead(const double*, const double*, long long, int, const double*, const double*,
                                      const double*, const double*, const double*, int, const cngp_stop_config*, int*,
-                                     int*, int*, double*, unsigned long long*, cudaStream_t);
+                                     int*, int*, double*, unsigned long long*, double*, double*, double*, cudaStream_t);
 extern "C" int cngp_launch_llh_to_enu(const double*, long long, const cngp_stop_config*, double*, cudaStream_t);
 extern "C" int cngp_launch_ekf_context(const double*, const double*, const double*, const double*, long long, double, double,
                                        double*, double*, double*, cudaStream_t);
@@ -784,7 +784,17 @@ extern "C" int cngp_zupt_lookahead_batch(cngp_ctx* ctx, const double* mean, cons
                                          const double* pos, int32_t per_window, const cngp_stop_config* cfg,
                                          int32_t* triggered, int32_t* i_stop, int32_t* step_stop, double* xy_err,
                                          int32_t mem) {
+  return cngp_zupt_lookahead_batch_ex(ctx, mean, sigma, B, M, P, Q, STM, Hvec, pos, per_window, cfg, triggered, i_stop,
+                                      step_stop, xy_err, nullptr, nullptr, nullptr, mem);
+}
+
+extern "C" int cngp_zupt_lookahead_batch_ex(cngp_ctx* ctx, const double* mean, const double* sigma, int64_t B, int32_t M,
+                                            const double* P, const double* Q, const double* STM, const double* Hvec,
+                                            const double* pos, int32_t per_window, const cngp_stop_config* cfg,
+                                            int32_t* triggered, int32_t* i_stop, int32_t* step_stop, double* xy_err,
+                                            double* P_final, double* K_final, double* R_final, int32_t mem) {
   if (!ctx) return CNGP_ERR_INVALID;
+  if ((K_final || R_final) && !P_final) return fail(ctx, CNGP_ERR_INVALID, "lookahead: K_final / R_final need P_final");
   if (!mean || !sigma || !P || !Q || !STM || !Hvec || !pos || !triggered || !i_stop || B < 0 || M <= 0)
     return fail(ctx, CNGP_ERR_INVALID, "lookahead: bad argument");
   if (B == 0) return CNGP_OK;
@@ -812,8 +822,14 @@ extern "C" int cngp_zupt_lookahead_batch(cngp_ctx* ctx, const double* mean, cons
   ctx->begin(CNGP_PROF_LOOKAHEAD);
   unsigned long long* d_counter = (unsigned long long*)ctx->buf(17, 64);
   if (!d_counter) return fail(ctx, CNGP_ERR_NOMEM, "lookahead: work counter");
+  double* d_Pf = (double*)st.out(P_final, sizeof(double) * 225 * (size_t)B);
+  double* d_Kf = (double*)st.out(K_final, sizeof(double) * 60 * (size_t)B);
+  double* d_Rf = (double*)st.out(R_final, sizeof(double) * 16 * (size_t)B);
+  if (st.err) return fail(ctx, st.err, "lookahead: staging failed");
+  if (d_Kf) CU(ctx, cudaMemsetAsync(d_Kf, 0, sizeof(double) * 60 * (size_t)B, ctx->stream));   // windows without an update
+  if (d_Rf) CU(ctx, cudaMemsetAsync(d_Rf, 0, sizeof(double) * 16 * (size_t)B, ctx->stream));
   const int e = cngp_launch_lookahead(d_mean, d_sigma, B, M, d_P, d_Q, d_F, d_H, d_pos, per_window, &c, d_trig, d_i,
-                                      d_step, d_xy, d_counter, ctx->stream);
+                                      d_step, d_xy, d_counter, d_Pf, d_Kf, d_Rf, ctx->stream);
   ctx->end();
   if (e) return fail(ctx, CNGP_ERR_CUDA, "lookahead launch: %s", cudaGetErrorString((cudaError_t)e));
   const int rc = st.finish();

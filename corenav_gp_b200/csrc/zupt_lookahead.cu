@@ -28,6 +28,9 @@ struct LookaheadArgs {
   cngp_stop_config cfg;
   int* triggered; int* i_stop; int* step_stop; double* xy_err;
   unsigned long long* next_window;   // tensor-core kernel: work counter (windows are claimed one at a time), or null
+  // optional final state per window (the reference leaves it in public members, gp_predictor.h:36-43): P_pred after the
+  // last step executed, K_pred and R_IP of the last update - row-major [225], [60] (15 x 4), [16]
+  double* P_final; double* K_final; double* R_final;
 };
 
 struct LlhConst {
@@ -509,6 +512,12 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 2) zupt_lookahead_tc_kernel(con
     a.step_stop[b] = step;
     a.xy_err[b] = xy;
   }
+  if (a.P_final) {
+    __syncwarp();
+    for (int i = lane; i < 225; i += 32) a.P_final[b * 225 + i] = Ps[(i / 15) * TC_LD + i % 15];
+    if (a.K_final) for (int i = lane; i < 60; i += 32) a.K_final[b * 60 + i] = Ks[(i / 4) * TC_LD4 + i % 4];
+    if (a.R_final && lane < 16) a.R_final[b * 16 + lane] = Rs[lane];
+  }
   if (!a.next_window) return;
   }   // next claimed window
 }
@@ -749,6 +758,12 @@ __global__ void __launch_bounds__(LA_WARPS * 32) zupt_lookahead_kernel(const Loo
     a.step_stop[b] = step;
     a.xy_err[b] = xy;
   }
+  if (a.P_final) {
+    __syncwarp();
+    for (int i = lane; i < 225; i += 32) a.P_final[b * 225 + i] = P[i];
+    if (a.K_final) for (int i = lane; i < 60; i += 32) a.K_final[b * 60 + i] = K[i];
+    if (a.R_final && lane < 16) a.R_final[b * 16 + lane] = R[lane];
+  }
 }
 
 // Small batches (the reference's own use: ONE window per callback, gp_predictor.cpp:16): the look-ahead is a chain of up
@@ -918,6 +933,12 @@ __global__ void __launch_bounds__(LA_CTA_THREADS) zupt_lookahead_cta_kernel(cons
     a.step_stop[b] = step;
     a.xy_err[b] = xy;
   }
+  if (a.P_final) {
+    __syncthreads();
+    if (tid < 225) a.P_final[b * 225 + tid] = P[tid];
+    if (a.K_final && tid < 60) a.K_final[b * 60 + tid] = K[tid];
+    if (a.R_final && tid < 16) a.R_final[b * 16 + tid] = R[tid];
+  }
 }
 
 __global__ void llh_to_enu_kernel(const double* llh, long long n, cngp_stop_config cfg, double* enu) {
@@ -935,9 +956,10 @@ extern "C" int cngp_launch_lookahead(const double* mean, const double* sigma, lo
                                      const double* Q, const double* STM, const double* Hvec, const double* pos,
                                      int per_window, const cngp_stop_config* cfg, int* triggered, int* i_stop,
                                      int* step_stop, double* xy_err, unsigned long long* work_counter,
-                                     cudaStream_t stream) {
+                                     double* P_final, double* K_final, double* R_final, cudaStream_t stream) {
   using namespace cngp;
-  LookaheadArgs a{mean, sigma, B, M, P, Q, STM, Hvec, pos, per_window, *cfg, triggered, i_stop, step_stop, xy_err, nullptr};
+  LookaheadArgs a{mean, sigma, B, M, P, Q, STM, Hvec, pos, per_window, *cfg, triggered, i_stop, step_stop, xy_err, nullptr,
+                  P_final, K_final, R_final};
   const size_t smem = (size_t)LA_WARPS * LA_WS * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {

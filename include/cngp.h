@@ -200,13 +200,23 @@ void cngp_default_stop_config(cngp_stop_config* c);
  *   mean, sigma [B][M] (GP_Output); P, Q, STM [.][225] row-major 15x15; Hvec [.][60]; pos [.][3] (lat, lon, h)
  *   triggered [B] 0/1; i_stop [B] = odometry updates performed when the loop ended (the reference's `i`);
  *   step_stop [B] = slip_i at the trigger or ratio*M; xy_err [B] = last horizontal error computed.
- * Batches of up to 592 windows run one CTA per window (the reference's single callback: 1.7 ms instead of 3.6 ms), larger
- * ones one warp per window; both produce the same bits.  Test hook: the environment variable CNGP_LOOKAHEAD_KERNEL
- * ("warp" / "cta") forces one of the two. */
+ * The 15 x 15 algebra runs on the FP64 tensor cores (one mma.sync.m8n8k4.f64 is bit for bit an ascending fma chain, the
+ * order the oracle uses); one warp per window, windows claimed dynamically.  Test hook: the environment variable
+ * CNGP_LOOKAHEAD_KERNEL ("tc" default / "warp" / "cta") selects the tensor-core kernel or one of the two scalar kernels of
+ * round 1; all three produce the same bits. */
 int cngp_zupt_lookahead_batch(cngp_ctx* ctx, const double* mean, const double* sigma, int64_t B, int32_t M,
                               const double* P, const double* Q, const double* STM, const double* Hvec,
                               const double* pos, int32_t per_window, const cngp_stop_config* cfg,
                               int32_t* triggered, int32_t* i_stop, int32_t* step_stop, double* xy_err, int32_t mem);
+
+/* The same, also returning what the reference leaves in GpPredictor's public members after the callback
+ * (gp_predictor.h:36-43): P_final [B][225] = P_pred after the last step executed, K_final [B][60] = K_pred (15 x 4) and
+ * R_final [B][16] = R_IP of the last update; each may be NULL (K_final / R_final need P_final). */
+int cngp_zupt_lookahead_batch_ex(cngp_ctx* ctx, const double* mean, const double* sigma, int64_t B, int32_t M,
+                                 const double* P, const double* Q, const double* STM, const double* Hvec,
+                                 const double* pos, int32_t per_window, const cngp_stop_config* cfg,
+                                 int32_t* triggered, int32_t* i_stop, int32_t* step_stop, double* xy_err,
+                                 double* P_final, double* K_final, double* R_final, int32_t mem);
 
 /* GpPredictor::llh_to_enu for n points on the device (lat, lon, h -> E, N, U); llh, enu [n][3]. */
 int cngp_llh_to_enu(cngp_ctx* ctx, const double* llh, int64_t n, const cngp_stop_config* cfg, double* enu, int32_t mem);

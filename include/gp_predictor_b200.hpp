@@ -83,9 +83,14 @@ class GpPredictor {
   Vector3 llh_to_enu(const double latitude, const double longitude, const double height);
 
   core_nav::GP_Output gp_data_;
+  // gp_predictor.h:36-43.  Row-major arrays stand in for the Eigen matrices.  After GPCallBack they hold what the
+  // reference's members hold: P_pred the covariance after the last look-ahead step executed, K_pred / R_IP / R_IP_2 the
+  // gain and the odometry noise of the last update, R_IP_1 the constant wheel-geometry matrix (gp_predictor.cpp:84-87).
+  std::array<double, 16> R_IP{}, R_IP_1{}, R_IP_2{};
+  std::array<double, 60> K_pred{};    // 15 x 4
   std::array<double, 60> H_{};        // as received: HvecData (the kernel applies the reference's index)
   std::array<double, 225> P_pred{}, STM_{}, Q_{};
-  Vector3 savePos{};
+  Vector3 savePos{}, ins_enu_slip{}, ins_enu_slip3p{}, ins_enu_slip_3p{};   // gp_predictor.cpp:95-97
   std_msgs::Float64 stop_cmd_msg_;
   bool new_gp_data_arrived_ = false;
   double gp_arrived_time_ = 0.0;

@@ -209,7 +209,7 @@ static void propagate(double P[15][15], const double F[15][15], const double Q[1
     }
 }
 
-static void joseph_update(double P[15][15], const double H[4][15], const double R[4][4]) {
+static void joseph_update(double P[15][15], const double H[4][15], const double R[4][4], double* K_out) {
   double PHt[15][4], HP[4][15], S[4][4], Si[4][4], K[15][4], IKH[15][15], T[15][15], KR[15][4];
   for (int r = 0; r < 15; ++r)
     for (int m = 0; m < 4; ++m) {
@@ -262,6 +262,9 @@ static void joseph_update(double P[15][15], const double H[4][15], const double 
       for (int n = 0; n < 4; ++n) a2 = fma(KR[r][n], K[c][n], a2);
       P[r][c] = a1 + a2;
     }
+  if (K_out)
+    for (int r = 0; r < 15; ++r)
+      for (int m = 0; m < 4; ++m) K_out[r * 4 + m] = K[r][m];
 }
 
 /* GpPredictor::GPCallBack look-ahead (gp_predictor.cpp:64-124) for one window.
@@ -271,11 +274,27 @@ static void joseph_update(double P[15][15], const double H[4][15], const double 
  * reference's `i`), *step_stop = slip_i at the trigger (or 5*M if none), *xy_err = last xy error computed,
  * xy_trace (optional, length ratio*M) = xy error per step, P_out (optional, 225) = final covariance.
  */
+int stop_oracle_lookahead_ex(const double* mean, const double* sigma, int M,
+                             const double* Pvec, const double* Qvec, const double* STMvec, const double* Hvec,
+                             const double* pos, const stop_cfg* c,
+                             int* triggered, int* i_stop, int* step_stop, double* xy_err,
+                             double* xy_trace, double* P_out, double* K_out, double* R_out);
+
 int stop_oracle_lookahead(const double* mean, const double* sigma, int M,
                           const double* Pvec, const double* Qvec, const double* STMvec, const double* Hvec,
                           const double* pos, const stop_cfg* c,
                           int* triggered, int* i_stop, int* step_stop, double* xy_err,
                           double* xy_trace, double* P_out) {
+  return stop_oracle_lookahead_ex(mean, sigma, M, Pvec, Qvec, STMvec, Hvec, pos, c, triggered, i_stop, step_stop, xy_err,
+                                  xy_trace, P_out, 0, 0);
+}
+
+/* the same, also returning the reference's public members K_pred (15 x 4) and R_IP (4 x 4) of the last update */
+int stop_oracle_lookahead_ex(const double* mean, const double* sigma, int M,
+                             const double* Pvec, const double* Qvec, const double* STMvec, const double* Hvec,
+                             const double* pos, const stop_cfg* c,
+                             int* triggered, int* i_stop, int* step_stop, double* xy_err,
+                             double* xy_trace, double* P_out, double* K_out, double* R_out) {
   double P[15][15], Q[15][15], F[15][15], H[4][15];
   for (int r = 0; r < 15; ++r)
     for (int col = 0; col < 15; ++col) {
@@ -293,7 +312,10 @@ int stop_oracle_lookahead(const double* mean, const double* sigma, int M,
     propagate(P, F, Q);
     if (slip_i % c->ratio == 0) {
       stop_oracle_ut_R(mean[i], sigma[i], c, R);
-      joseph_update(P, H, R);
+      joseph_update(P, H, R, K_out);
+      if (R_out)
+        for (int a = 0; a < 4; ++a)
+          for (int b = 0; b < 4; ++b) R_out[a * 4 + b] = R[a][b];
       i++;
     }
     stop_oracle_llh_to_enu(pos[0] + 3.0 * sqrt(fabs(P[6][6])), pos[1] + 3.0 * sqrt(fabs(P[7][7])),

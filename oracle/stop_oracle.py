@@ -95,14 +95,14 @@ def lookahead(mean, sigma, P, Q, STM, Hvec, pos, cfg=None, want_trace=False):
     trig, i_stop, step = C.c_int(), C.c_int(), C.c_int()
     xy = C.c_double()
     trace = np.full(cfg.ratio * M, np.nan) if want_trace else None
-    P_out = np.zeros(225)
-    f = lib().stop_oracle_lookahead
+    P_out, K_out, R_out = np.zeros(225), np.zeros(60), np.zeros(16)
+    f = lib().stop_oracle_lookahead_ex
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(StopCfg)] + \
-                 [C.POINTER(C.c_int)] * 3 + [C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+                 [C.POINTER(C.c_int)] * 3 + [C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     f(_p(mean), _p(sigma), M, *[_p(a) for a in arrs], C.byref(cfg), C.byref(trig), C.byref(i_stop), C.byref(step),
-      C.byref(xy), _p(trace) if want_trace else None, _p(P_out))
+      C.byref(xy), _p(trace) if want_trace else None, _p(P_out), _p(K_out), _p(R_out))
     out = dict(triggered=bool(trig.value), i_stop=i_stop.value, step_stop=step.value, xy_err=xy.value,
-               P=P_out.reshape(15, 15))
+               P=P_out.reshape(15, 15), K=K_out.reshape(15, 4), R=R_out.reshape(4, 4))
     if want_trace:
         out["xy_trace"] = trace
     return out

@@ -53,9 +53,24 @@ int main(int argc, char** argv) {
   const bool ret = node.GPCallBack(msg);
   const GpPredictor::Vector3 enu = node.llh_to_enu(node.savePos[0], node.savePos[1], node.savePos[2] + 1.0);
   printf("{\"returned\": %d, \"published\": %d, \"stop_cmd\": %.17g, \"i\": %d, \"slip_i\": %d, \"xy_errSlip\": %.17g, "
-         "\"flag\": %d, \"enu_up\": [%.17g, %.17g, %.17g]}\n",
+         "\"flag\": %d, \"enu_up\": [%.17g, %.17g, %.17g]",
          (int)ret, published, stop_cmd, node.i, node.slip_i, node.xy_errSlip, (int)node.new_gp_data_arrived_, enu[0], enu[1],
          enu[2]);
+  // the public matrix members of gp_predictor.h:36-46 after the callback
+  auto dump = [](const char* name, const double* v, int n) {
+    printf(", \"%s\": [", name);
+    for (int k = 0; k < n; ++k) printf("%s%.17g", k ? ", " : "", v[k]);
+    printf("]");
+  };
+  dump("P_pred", node.P_pred.data(), 225);
+  dump("K_pred", node.K_pred.data(), 60);
+  dump("R_IP", node.R_IP.data(), 16);
+  dump("R_IP_1", node.R_IP_1.data(), 16);
+  dump("R_IP_2", node.R_IP_2.data(), 16);
+  dump("ins_enu_slip", node.ins_enu_slip.data(), 3);
+  dump("ins_enu_slip3p", node.ins_enu_slip3p.data(), 3);
+  dump("ins_enu_slip_3p", node.ins_enu_slip_3p.data(), 3);
+  printf("}\n");
   cngp_destroy(ctx);
   return 0;
 }

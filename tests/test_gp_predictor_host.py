@@ -52,12 +52,23 @@ def run(exe, path, advance, service_ok=1):
 def check_against_oracle(exe, tmp_path):
     path = str(tmp_path / "case.bin")
     mean, sigma, c = write_case(path, M=120, s0=0.7)
-    ref = so.lookahead(mean, sigma, c["P"], c["Q"], c["STM"], c["Hvec"], c["pos"])
+    ref = so.lookahead(mean, sigma, c["P"], c["Q"], c["STM"], c["Hvec"], c["pos"], so.default_cfg(trig_mode=1))
     assert ref["triggered"]
     out = run(exe, path, advance=0.25)
     assert out["returned"] == 1 and out["published"] == 1 and out["flag"] == 0
     assert out["i"] == ref["i_stop"] and out["slip_i"] == ref["step_stop"]
-    assert abs(out["xy_errSlip"] - ref["xy_err"]) < 1e-8
+    assert out["xy_errSlip"] == ref["xy_err"]
+    # public matrix members after the callback (gp_predictor.h:36-46): P_pred is left at the final look-ahead covariance,
+    # K_pred / R_IP / R_IP_2 at the last update, ins_enu_slip* at the last error-observer evaluation
+    assert np.array_equal(np.array(out["P_pred"]).reshape(15, 15), ref["P"])
+    assert np.array_equal(np.array(out["K_pred"]).reshape(15, 4), ref["K"])
+    assert np.array_equal(np.array(out["R_IP"]).reshape(4, 4), ref["R"])
+    R1 = np.array(out["R_IP_1"]).reshape(4, 4)
+    R2 = np.array(out["R_IP_2"]).reshape(4, 4)
+    assert np.allclose(25.0 * R1 @ R2 @ R1.T, ref["R"], rtol=1e-14, atol=0)          # gp_predictor.cpp:88
+    e0, e3 = np.array(out["ins_enu_slip"]), np.array(out["ins_enu_slip3p"])
+    assert abs(np.hypot(*(e3 - e0)[:2]) - ref["xy_err"]) < 1e-9                      # gp_predictor.cpp:99
+    assert np.all(np.array(out["ins_enu_slip_3p"]) != e3)
     # gp_predictor.cpp:107-116: stop in (t_gp + i/10 - now) seconds ...
     assert out["stop_cmd"] == pytest.approx(ref["i_stop"] / 10.0 - 0.25, abs=1e-12)
     # ... or 0.5 s when that moment has already passed

@@ -165,3 +165,23 @@ def test_tensor_core_kernel_many_windows_per_cta_and_monte_carlo_contexts(gp_ctx
     assert 0 < ref["triggered"].sum() < B
     for k in ("triggered", "i_stop", "step_stop", "xy_err"):
         assert np.array_equal(out[k], ref[k]), k
+
+
+@pytest.mark.parametrize("kernel", ["tc", "warp", "cta"])
+def test_final_state_matches_the_reference_members(gp_ctx, monkeypatch, kernel):
+    """cngp_zupt_lookahead_batch_ex: P_pred / K_pred / R_IP as the reference leaves them in its public members after the
+    callback (gp_predictor.h:36-43) - against the oracle bit for bit, and against the values the reference binary itself
+    produced (golden file, 1e-12: only the rounding inside a matrix product differs)."""
+    import os
+    monkeypatch.setenv("CNGP_LOOKAHEAD_KERNEL", kernel)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "stop_ref_golden.npz"))
+    out = gp_ctx.zupt_lookahead(g["mean"], g["sigma"], g["P"], g["Q"], g["STM"], g["Hvec"], g["pos"], want_state=True)
+    scale = np.abs(g["P_final"]).max(axis=1, keepdims=True)
+    assert np.max(np.abs(out["P_final"] - g["P_final"]) / scale) < 1e-12
+    assert np.max(np.abs(out["K_final"] - g["K_final"]) / np.abs(g["K_final"]).max(axis=1, keepdims=True)) < 1e-11
+    assert np.max(np.abs(out["R_final"] - g["R_final"]) / np.abs(g["R_final"]).max(axis=1, keepdims=True)) < 1e-14
+    for b in (0, 5, 17, 40):
+        o = so.lookahead(g["mean"][b], g["sigma"][b], g["P"][b], g["Q"][b], g["STM"][b], g["Hvec"][b], g["pos"][b], ocfg())
+        assert np.array_equal(out["P_final"][b].reshape(15, 15), o["P"])
+        assert np.array_equal(out["K_final"][b].reshape(15, 4), o["K"])
+        assert np.array_equal(out["R_final"][b].reshape(4, 4), o["R"])
