@@ -78,6 +78,7 @@ SIGNATURES = {
                                             C.POINTER(StopConfig), c_ip, c_ip, c_ip, c_dp, c_i32]),
     "cngp_zupt_lookahead_batch_ex": (C.c_int, [c_vp, c_dp, c_dp, c_i64, c_i32, c_dp, c_dp, c_dp, c_dp, c_dp, c_i32,
                                                C.POINTER(StopConfig), c_ip, c_ip, c_ip, c_dp, c_dp, c_dp, c_dp, c_i32]),
+    "cngp_ekf_covariance_batch": (C.c_int, [c_vp, c_dp, c_dp, c_dp, c_dp, c_dp, c_i64, c_i32, c_i32, c_i32, c_dp, c_i32]),
     "cngp_llh_to_enu": (C.c_int, [c_vp, c_dp, c_i64, C.POINTER(StopConfig), c_dp, c_i32]),
     "cngp_ekf_context_batch": (C.c_int, [c_vp, c_dp, c_dp, c_dp, c_dp, c_i64, C.c_double, C.c_double, c_dp, c_dp, c_dp,
                                          c_i32]),

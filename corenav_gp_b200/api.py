@@ -310,6 +310,29 @@ class GpContext:
         self._check(rc, "cngp_zupt_lookahead_batch")
         return dict(triggered=trig, i_stop=i_stop, step_stop=step, xy_err=xy)
 
+    def ekf_covariance(self, P0, Q, STM, H, R, n_steps: int, ratio: int = 5):
+        """The EKF's covariance recursion (CoreNav.cpp:101, 226-230) for B operating points: n_steps IMU steps with an
+        odometry update every `ratio`-th.  P0 [B,225]; Q, STM ([225] or [B,225]); H ([60] true row-major 4x15 or [B,60]);
+        R ([16] or [B,16]).  Returns P [B,225] - the P_pred of the SetStopping service (CoreNav.cpp:291-292)."""
+        dev = _is_cuda(P0)
+        B = P0.shape[0]
+        mask = 1                                   # P0 is per window
+        args = [_Arg(P0, np.float64, dev)]
+        for bit, (arr, sz) in ((1, (Q, 225)), (2, (STM, 225)), (3, (H, 60)), (4, (R, 16))):
+            n_el = int(np.prod(tuple(arr.shape)))
+            if n_el == sz * B and (B > 1 or len(arr.shape) >= 2):
+                mask |= 1 << bit
+            elif n_el != sz:
+                raise CngpError(f"ekf_covariance: array {bit} has {n_el} elements, expected {sz} or [{B},{sz}]")
+            args.append(_Arg(arr, np.float64, dev))
+        out = self._empty((B, 225), np.float64, dev)
+        o = _Arg(out, np.float64, dev, output=True)
+        self._bind_stream(dev)
+        rc = self.lib.cngp_ekf_covariance_batch(self.h, *[a.ptr for a in args], B, n_steps, ratio, mask, o.ptr,
+                                                L.MEM_DEVICE if dev else L.MEM_HOST)
+        self._check(rc, "cngp_ekf_covariance_batch")
+        return out
+
     def ekf_context(self, llh, vel, att, f_ib_b, dt: float = 0.02, dt_odo: float = 0.1, want_h: bool = True):
         """STM, Q (and the packed odometry H) of the SetStopping service for B operating points
         (CoreNav::insErrorStateModel_LNF / calc_Q, CoreNav.cpp:411-527).  Inputs [B,3]; returns (STM [B,225], Q [B,225],

@@ -20,7 +20,8 @@
 
 extern "C" int cngp_launch_lookahead(const double*, const double*, long long, int, const double*, const double*,
                                      const double*, const double*, const double*, int, const cngp_stop_config*, int*,
-                                     int*, int*, double*, unsigned long long*, double*, double*, double*, cudaStream_t);
+                                     int*, int*, double*, unsigned long long*, double*, double*, double*, const double*, int,
+                                     cudaStream_t);
 extern "C" int cngp_launch_llh_to_enu(const double*, long long, const cngp_stop_config*, double*, cudaStream_t);
 extern "C" int cngp_launch_ekf_context(const double*, const double*, const double*, const double*, long long, double, double,
                                        double*, double*, double*, cudaStream_t);
@@ -829,11 +830,61 @@ extern "C" int cngp_zupt_lookahead_batch_ex(cngp_ctx* ctx, const double* mean, c
   if (d_Kf) CU(ctx, cudaMemsetAsync(d_Kf, 0, sizeof(double) * 60 * (size_t)B, ctx->stream));   // windows without an update
   if (d_Rf) CU(ctx, cudaMemsetAsync(d_Rf, 0, sizeof(double) * 16 * (size_t)B, ctx->stream));
   const int e = cngp_launch_lookahead(d_mean, d_sigma, B, M, d_P, d_Q, d_F, d_H, d_pos, per_window, &c, d_trig, d_i,
-                                      d_step, d_xy, d_counter, d_Pf, d_Kf, d_Rf, ctx->stream);
+                                      d_step, d_xy, d_counter, d_Pf, d_Kf, d_Rf, nullptr, 0, ctx->stream);
   ctx->end();
   if (e) return fail(ctx, CNGP_ERR_CUDA, "lookahead launch: %s", cudaGetErrorString((cudaError_t)e));
   const int rc = st.finish();
   if (rc) return fail(ctx, rc, "lookahead: copy-out failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return CNGP_OK;
+}
+
+// The filter's own covariance recursion for B operating points (the P half): n_steps IMU steps of
+// P <- STM P STM' + Q (CoreNav.cpp:101) with the odometry update's Joseph form every `ratio`-th step
+// (K = P H'(H P H' + R)^-1, P <- (I-KH) P (I-KH)' + K R K', CoreNav.cpp:226-230) - what stands in P_ when
+// CoreNav::Update copies it to P_pred for the SetStopping service (CoreNav.cpp:291-292).  Runs on the tensor-core
+// look-ahead kernel with the true 4 x 15 H (row-major), the filter's constant R and no error observer.
+extern "C" int cngp_ekf_covariance_batch(cngp_ctx* ctx, const double* P0, const double* Q, const double* STM,
+                                         const double* H, const double* R, int64_t B, int32_t n_steps, int32_t ratio,
+                                         int32_t per_window, double* P_out, int32_t mem) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!P0 || !Q || !STM || !H || !R || !P_out || B < 0 || n_steps <= 0 || ratio <= 0 || n_steps % ratio != 0)
+    return fail(ctx, CNGP_ERR_INVALID, "ekf_covariance: bad argument (n_steps must be a positive multiple of ratio)");
+  if (B == 0) return CNGP_OK;
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  cngp_stop_config c;
+  cngp_default_stop_config(&c);
+  c.ratio = ratio;
+  c.fix_h_packing = 1;                       // H is given as the true row-major 4 x 15 matrix
+  c.thresh = 1e300;                          // no trigger: all n_steps are executed
+  const int M = n_steps / ratio;
+  Stage st{ctx, mem};
+  auto cnt = [&](int bit, size_t sz) { return sizeof(double) * sz * ((per_window & bit) ? (size_t)B : 1); };
+  const double* d_P = (const double*)st.in(P0, cnt(CNGP_PERWIN_P, 225));
+  const double* d_Q = (const double*)st.in(Q, cnt(CNGP_PERWIN_Q, 225));
+  const double* d_F = (const double*)st.in(STM, cnt(CNGP_PERWIN_STM, 225));
+  const double* d_H = (const double*)st.in(H, cnt(CNGP_PERWIN_H, 60));
+  const double* d_R = (const double*)st.in(R, cnt(CNGP_PERWIN_POS, 16));     // the R bit re-uses the position slot
+  double* d_out = (double*)st.out(P_out, sizeof(double) * 225 * (size_t)B);
+  if (st.err) return fail(ctx, st.err, "ekf_covariance: staging failed");
+  // the slip arrays are not used on this path (fixed R) and the observer cannot trigger: they get harmless storage
+  double* d_ms = (double*)ctx->buf(18, sizeof(double) * (size_t)M);
+  int* d_i4 = (int*)ctx->buf(19, sizeof(int) * 3 * (size_t)B);
+  double* d_xy = (double*)ctx->buf(13, sizeof(double) * (size_t)B);
+  double* d_pos = (double*)ctx->buf(14, sizeof(double) * 3);
+  unsigned long long* d_counter = (unsigned long long*)ctx->buf(17, 64);
+  if (!d_ms || !d_i4 || !d_xy || !d_pos || !d_counter) return fail(ctx, CNGP_ERR_NOMEM, "ekf_covariance: buffers");
+  CU(ctx, cudaMemsetAsync(d_ms, 0, sizeof(double) * (size_t)M, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(d_pos, c.init_llh, sizeof(double) * 3, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->begin(CNGP_PROF_LOOKAHEAD);
+  const int pw = per_window & (CNGP_PERWIN_P | CNGP_PERWIN_Q | CNGP_PERWIN_STM | CNGP_PERWIN_H);
+  // mean / sigma: one zero row shared by every window (M < 0 = row stride 0)
+  const int e = cngp_launch_lookahead(d_ms, d_ms, B, -M, d_P, d_Q, d_F, d_H, d_pos, pw, &c, d_i4, d_i4 + B, d_i4 + 2 * B,
+                                      d_xy, d_counter, d_out, nullptr, nullptr, d_R, (per_window & CNGP_PERWIN_POS) ? 1 : 0,
+                                      ctx->stream);
+  ctx->end();
+  if (e) return fail(ctx, CNGP_ERR_CUDA, "ekf_covariance launch: %s", cudaGetErrorString((cudaError_t)e));
+  const int rc = st.finish();
+  if (rc) return fail(ctx, rc, "ekf_covariance: copy-out failed: %s", cudaGetErrorString(cudaGetLastError()));
   return CNGP_OK;
 }
 

@@ -31,6 +31,10 @@ struct LookaheadArgs {
   // optional final state per window (the reference leaves it in public members, gp_predictor.h:36-43): P_pred after the
   // last step executed, K_pred and R_IP of the last update - row-major [225], [60] (15 x 4), [16]
   double* P_final; double* K_final; double* R_final;
+  // EKF covariance recursion (cngp_ekf_covariance_batch): a fixed odometry noise R [16] or [B][16] replaces the UT of the
+  // predicted slip (CoreNav.cpp:228 uses the filter's constant R_), tensor-core kernel only
+  const double* R_fixed; int R_per_window;
+  long long ms_stride;   // row stride of mean / sigma: M, or 0 when every window shares one row
 };
 
 struct LlhConst {
@@ -302,8 +306,8 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 2) zupt_lookahead_tc_kernel(con
   const ObsBound ob = obs_prepare(lat, lon, hgt, cfg);
   __syncwarp();
 
-  const double* mean = a.mean + b * a.M;
-  const double* sigma = a.sigma + b * a.M;
+  const double* mean = a.mean + b * a.ms_stride;
+  const double* sigma = a.sigma + b * a.ms_stride;
   const int nsteps = cfg.ratio * a.M;
   int i_upd = 0, trig = 0, step = nsteps;
   double xy = 0.0;
@@ -370,6 +374,10 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 2) zupt_lookahead_tc_kernel(con
           const double bm = (cfg.scale * r1(g, k)) * R2[k];
           acc0 = fma(bm, r1(2 * t, k), acc0);
           acc1 = fma(bm, r1(2 * t + 1, k), acc1);
+        }
+        if (a.R_fixed && g < 4 && t < 2) {
+          const double* rf = a.R_fixed + (a.R_per_window ? b * 16 : 0);
+          acc0 = rf[g * 4 + 2 * t]; acc1 = rf[g * 4 + 2 * t + 1];
         }
         if (g < 4 && t < 2) { Rs[g * 4 + 2 * t] = acc0; Rs[g * 4 + 2 * t + 1] = acc1; }
       }
@@ -566,8 +574,8 @@ __global__ void __launch_bounds__(LA_WARPS * 32) zupt_lookahead_kernel(const Loo
   }
   const bool bias_rows_identity = __all_sync(0xffffffffu, unit_ok);
 
-  const double* mean = a.mean + b * a.M;
-  const double* sigma = a.sigma + b * a.M;
+  const double* mean = a.mean + b * a.ms_stride;
+  const double* sigma = a.sigma + b * a.ms_stride;
   const int nsteps = cfg.ratio * a.M;
   int i_upd = 0, trig = 0, step = nsteps;
   double xy = 0.0;
@@ -805,8 +813,8 @@ __global__ void __launch_bounds__(LA_CTA_THREADS) zupt_lookahead_cta_kernel(cons
   }
   const bool bias_rows_identity = __syncthreads_and(unit_ok);
 
-  const double* mean = a.mean + b * a.M;
-  const double* sigma = a.sigma + b * a.M;
+  const double* mean = a.mean + b * a.ms_stride;
+  const double* sigma = a.sigma + b * a.ms_stride;
   const int nsteps = cfg.ratio * a.M;
   const bool ent = tid < 225;
   const int rr = tid / 15, cc = tid % 15;      // entry (rr, cc) of a 15x15 matrix
@@ -956,10 +964,12 @@ extern "C" int cngp_launch_lookahead(const double* mean, const double* sigma, lo
                                      const double* Q, const double* STM, const double* Hvec, const double* pos,
                                      int per_window, const cngp_stop_config* cfg, int* triggered, int* i_stop,
                                      int* step_stop, double* xy_err, unsigned long long* work_counter,
-                                     double* P_final, double* K_final, double* R_final, cudaStream_t stream) {
+                                     double* P_final, double* K_final, double* R_final, const double* R_fixed,
+                                     int R_per_window, cudaStream_t stream) {
   using namespace cngp;
-  LookaheadArgs a{mean, sigma, B, M, P, Q, STM, Hvec, pos, per_window, *cfg, triggered, i_stop, step_stop, xy_err, nullptr,
-                  P_final, K_final, R_final};
+  // M < 0: |M| entries of mean / sigma shared by every window (cngp_ekf_covariance_batch)
+  LookaheadArgs a{mean, sigma, B, M < 0 ? -M : M, P, Q, STM, Hvec, pos, per_window, *cfg, triggered, i_stop, step_stop,
+                  xy_err, nullptr, P_final, K_final, R_final, R_fixed, R_per_window, M < 0 ? 0LL : (long long)M};
   const size_t smem = (size_t)LA_WARPS * LA_WS * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
@@ -967,7 +977,7 @@ extern "C" int cngp_launch_lookahead(const double* mean, const double* sigma, lo
     attr_set = true;
   }
   const char* force = getenv("CNGP_LOOKAHEAD_KERNEL");     // "tc" (default) / "warp" / "cta": tests run all on one batch
-  if (!force || force[0] == 't') {
+  if (!force || force[0] == 't' || R_fixed) {
     // few windows: one warp per CTA so that they spread over the SMs; many: eight warps per CTA
     const int wpc = B <= 4 * 148 ? 1 : TC_WARPS;
     const size_t tsm = (size_t)TC_WARPS * TC_WS * sizeof(double);

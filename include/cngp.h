@@ -218,6 +218,16 @@ int cngp_zupt_lookahead_batch_ex(cngp_ctx* ctx, const double* mean, const double
                                  int32_t* triggered, int32_t* i_stop, int32_t* step_stop, double* xy_err,
                                  double* P_final, double* K_final, double* R_final, int32_t mem);
 
+/* The filter's own covariance recursion for B operating points: n_steps IMU steps of
+ * P <- STM P STM' + Q (CoreNav.cpp:101) with the odometry update's Joseph form every ratio-th step (CoreNav.cpp:226-230)
+ * - the covariance CoreNav::Update hands to the SetStopping service as P_pred (CoreNav.cpp:291-292).
+ *   P0, Q, STM [.][225] row-major; H [.][60] the TRUE 4 x 15 measurement matrix, row-major (not the service's packing);
+ *   R [.][16] the filter's odometry noise; per_window: CNGP_PERWIN_P | _Q | _STM | _H as above, CNGP_PERWIN_POS for R;
+ *   n_steps must be a multiple of ratio; P_out [B][225]. */
+int cngp_ekf_covariance_batch(cngp_ctx* ctx, const double* P0, const double* Q, const double* STM, const double* H,
+                              const double* R, int64_t B, int32_t n_steps, int32_t ratio, int32_t per_window,
+                              double* P_out, int32_t mem);
+
 /* GpPredictor::llh_to_enu for n points on the device (lat, lon, h -> E, N, U); llh, enu [n][3]. */
 int cngp_llh_to_enu(cngp_ctx* ctx, const double* llh, int64_t n, const cngp_stop_config* cfg, double* enu, int32_t mem);
 

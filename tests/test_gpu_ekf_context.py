@@ -54,3 +54,38 @@ def test_generated_contexts_reproduce_zupt_decisions(gp_ctx):
     assert 0 < ref["triggered"].sum()
     for key in ("triggered", "i_stop", "step_stop"):
         assert np.array_equal(out[key], ref[key]), key
+
+
+def test_ekf_covariance_recursion_matches_numpy(gp_ctx):
+    """cngp_ekf_covariance_batch (row N4, the P half): P <- STM P STM' + Q every IMU step, Joseph-form odometry update
+    every 5th (CoreNav.cpp:101, 226-230), against a numpy transcription with matrix products (different summation
+    order: 1e-11)."""
+    B, n_steps = 5, 750                              # one 150-count recording window at 5 IMU steps per odometry update
+    c = syn.lookahead_context(syn.window_sigmas(0, B))
+    P0 = c["P"]
+    F, Q, H = c["STM"].reshape(15, 15), c["Q"].reshape(15, 15), c["H"]
+    R = np.diag([0.05 ** 2, 0.1 ** 2, 0.03 ** 2, 0.03 ** 2])
+    out = gp_ctx.ekf_covariance(P0, c["Q"], c["STM"], H.reshape(60), R.reshape(16), n_steps)
+    for b in range(B):
+        P = P0[b].reshape(15, 15).copy()
+        for k in range(n_steps):
+            P = F @ P @ F.T + Q
+            if k % 5 == 0:
+                K = P @ H.T @ np.linalg.inv(H @ P @ H.T + R)
+                A = np.eye(15) - K @ H
+                P = A @ P @ A.T + K @ R @ K.T
+        got = out[b].reshape(15, 15)
+        assert np.max(np.abs(got - P)) / np.max(np.abs(P)) < 1e-10
+    # per-window R and Q
+    Rb = np.stack([R.reshape(16) * (1 + 0.1 * b) for b in range(B)])
+    Qb = np.stack([c["Q"] * (1 + 0.2 * b) for b in range(B)])
+    out2 = gp_ctx.ekf_covariance(P0, Qb, c["STM"], H.reshape(60), Rb, 50)
+    P = P0[3].reshape(15, 15).copy()
+    Q3, R3 = Qb[3].reshape(15, 15), Rb[3].reshape(4, 4)
+    for k in range(50):
+        P = F @ P @ F.T + Q3
+        if k % 5 == 0:
+            K = P @ H.T @ np.linalg.inv(H @ P @ H.T + R3)
+            A = np.eye(15) - K @ H
+            P = A @ P @ A.T + K @ R3 @ K.T
+    assert np.max(np.abs(out2[3].reshape(15, 15) - P)) / np.max(np.abs(P)) < 1e-10
