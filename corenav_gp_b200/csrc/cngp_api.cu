@@ -549,9 +549,8 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
                 ctx->scratch_bytes, slack * 8 + per_problem);
   long long chunk = (long long)((ctx->scratch_bytes - slack * 8) / per_problem);
   cudaEvent_t pending_inputs = nullptr;
-  auto send_inputs = [&](long long w0, cudaStream_t s) -> int {   // x, y of the slab starting at w0
-    if (w0 >= B) return 0;
-    const long long nw = std::min<long long>(chunk, B - w0);
+  auto send_inputs = [&](long long w0, long long nw, cudaStream_t s) -> int {   // x, y of the slab [w0, w0 + nw)
+    if (w0 >= B || nw <= 0) return 0;
     const size_t off = (size_t)w0 * N, bytes = sizeof(double) * (size_t)nw * N;
     if (cudaMemcpyAsync((double*)d_x + off, x + off, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return 1;
     if (cudaMemcpyAsync((double*)d_y + off, y + off, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return 1;
@@ -560,15 +559,31 @@ int cngp_predict_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* th
   if (pipelined) {
     if (!ctx->copy_stream && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
       return fail(ctx, CNGP_ERR_CUDA, "predict: cudaStreamCreate failed");
-    chunk = std::min<long long>(chunk, (B + 3) / 4);
     st.forget(mean);
     st.forget(var);
-    if (send_inputs(0, ctx->stream)) return fail(ctx, CNGP_ERR_CUDA, "predict: input copy failed");
   }
-  for (long long w0 = 0; w0 < B; w0 += chunk) {
-    const long long nw = std::min<long long>(chunk, B - w0);
-    if (pipelined && w0 + chunk < B) {   // next slab's inputs travel while this slab computes
-      if (send_inputs(w0 + chunk, ctx->copy_stream)) return fail(ctx, CNGP_ERR_CUDA, "predict: input copy failed");
+  // Slab schedule.  Device calls: as many windows as the scratch holds.  Pipelined host calls: what cannot overlap is the
+  // upload of the FIRST slab and the download of the LAST one, so those two are short (about two waves of the
+  // one-CTA-per-window factorisation) and the slabs in between long, all but the last a multiple of the SM count.
+  std::vector<std::pair<long long, long long>> slabs;
+  {
+    const long long sm = g_sm_count;
+    const long long head = 2 * sm, mid = ((B - head) / 3 / sm) * sm;
+    if (pipelined && mid >= 2 * sm && mid <= chunk) {
+      slabs.push_back({0, head});
+      for (int k = 0; k < 3; ++k) slabs.push_back({head + k * mid, mid});
+      if (head + 3 * mid < B) slabs.push_back({head + 3 * mid, B - head - 3 * mid});
+    } else {
+      if (pipelined) chunk = std::min<long long>(chunk, (B + 3) / 4);
+      for (long long w0 = 0; w0 < B; w0 += chunk) slabs.push_back({w0, std::min<long long>(chunk, B - w0)});
+    }
+  }
+  if (pipelined && send_inputs(slabs[0].first, slabs[0].second, ctx->stream))
+    return fail(ctx, CNGP_ERR_CUDA, "predict: input copy failed");
+  for (size_t si = 0; si < slabs.size(); ++si) {
+    const long long w0 = slabs[si].first, nw = slabs[si].second;
+    if (pipelined && si + 1 < slabs.size()) {   // next slab's inputs travel while this slab computes
+      if (send_inputs(slabs[si + 1].first, slabs[si + 1].second, ctx->copy_stream)) return fail(ctx, CNGP_ERR_CUDA, "predict: input copy failed");
       cudaEvent_t arrived = ctx->get_event();
       CU(ctx, cudaEventRecord(arrived, ctx->copy_stream));
       pending_inputs = arrived;
