@@ -89,6 +89,8 @@ SIGNATURES = {
     "cngp_large_make_plan": (C.c_int, [c_i64, c_i32, c_i32, C.POINTER(LargePlan)]),
     "cngp_large_assemble": (C.c_int, [c_vp, C.POINTER(LargePlan), C.POINTER(Kernel), c_dp, c_dp, c_dp, c_dp]),
     "cngp_large_factor_panel": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_dp, c_dp, c_ip]),
+    "cngp_large_factor_panel_ex": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_dp, c_dp, c_ip, c_i32]),
+    "cngp_large_copy_back": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp]),
     "cngp_large_update": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_i64, c_i64]),
     "cngp_large_reduce": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_dp, c_ip, c_dp, c_dp]),
     "cngp_large_backsolve_step": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_dp, c_i64, c_dp, c_dp]),

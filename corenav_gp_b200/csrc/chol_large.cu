@@ -341,20 +341,28 @@ __global__ void __launch_bounds__(256) large_back_partial_kernel(const double* A
   }
 }
 
-// alpha_j = inv(L_jj)^T (z_j - sum_chunks partial)
-__global__ void __launch_bounds__(LG_NB) large_back_finish_kernel(const double* W, const double* zj, const double* partial,
-                                                                  double* alpha_j) {
+// alpha_j = inv(L_jj)^T (z_j - sum_chunks partial).  1024 threads: column c of the 256 x 256 inverse is summed in four
+// row segments of 64 (a single thread walking a whole column made this 39 us of pure load latency per block column -
+// 5 ms of the 128-step backward sweep).
+__global__ void __launch_bounds__(4 * LG_NB) large_back_finish_kernel(const double* W, const double* zj, const double* partial,
+                                                                      double* alpha_j) {
   __shared__ double t[LG_NB];
-  const int c = threadIdx.x;
-  double s = zj[c];
-  for (int ch = 0; ch < BACK_CHUNKS; ++ch) s -= partial[ch * LG_NB + c];
-  t[c] = s;
+  __shared__ double seg_sum[4][LG_NB];
+  const int c = threadIdx.x % LG_NB, seg = threadIdx.x / LG_NB;
+  if (seg == 0) {
+    double s = zj[c];
+    for (int ch = 0; ch < BACK_CHUNKS; ++ch) s -= partial[ch * LG_NB + c];
+    t[c] = s;
+  }
   __syncthreads();
   // alpha[c] = sum_row W[row][c] t[row];  W element (row, c) is in tile (k-tile c/8, row tile row/8)
   const double* wt = W + (long long)(c / 8) * LG_BT * 64 + (c % 8);
+  const int lo = max(c - (c % 8), seg * (LG_NB / 4)), hi = (seg + 1) * (LG_NB / 4);
   double acc = 0.0;
-  for (int row = c - (c % 8); row < LG_NB; ++row) acc = fma(wt[(row / 8) * 64 + (row % 8) * 8], t[row], acc);
-  alpha_j[c] = acc;
+  for (int row = lo; row < hi; ++row) acc = fma(wt[(row / 8) * 64 + (row % 8) * 8], t[row], acc);
+  seg_sum[seg][c] = acc;
+  __syncthreads();
+  if (seg == 0) alpha_j[c] = ((seg_sum[0][c] + seg_sum[1][c]) + seg_sum[2][c]) + seg_sum[3][c];
 }
 
 // r = Ky v with Ky evaluated on the fly; one warp per row
@@ -480,6 +488,28 @@ extern "C" int cngp_large_assemble(cngp_ctx* ctx, const cngp_large_plan* p, cons
 
 extern "C" int cngp_large_factor_panel(cngp_ctx* ctx, const cngp_large_plan* p, double* A, int64_t k, double* panel,
                                        double* winv, double* logdet, int32_t* status) {
+  return cngp_large_factor_panel_ex(ctx, p, A, k, panel, winv, logdet, status, 0);
+}
+
+// 4. of cngp_large_factor_panel on its own: the panel is this block column of L - copy it back under the diagonal block.
+// Nothing before the backward sweep reads it there, so the two-stream driver takes it off the panel chain.
+extern "C" int cngp_large_copy_back(cngp_ctx* ctx, const cngp_large_plan* p, double* A, int64_t k, const double* panel) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!p || !A || !panel || k < 0 || k >= p->n_blockcols) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_copy_back: bad argument");
+  if (k % p->world != p->rank) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_copy_back: not the owner of this block column");
+  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
+  const long long l = k / p->world, cstride = p->row_tiles * 64;
+  double* Acol = A + l * LG_BT * cstride;
+  const long long r0 = k * LG_BT + LG_BT;
+  const long long pstride = (p->row_tiles - r0) * 64;
+  if (p->row_tiles - r0 <= 0) return CNGP_OK;
+  LCU(ctx, cudaMemcpy2DAsync(Acol + r0 * 64, cstride * 8, panel, pstride * 8, (size_t)(p->row_tiles - r0) * 512, LG_BT,
+                             cudaMemcpyDeviceToDevice, cngp_ctx_stream(ctx)));
+  return CNGP_OK;
+}
+
+extern "C" int cngp_large_factor_panel_ex(cngp_ctx* ctx, const cngp_large_plan* p, double* A, int64_t k, double* panel,
+                                          double* winv, double* logdet, int32_t* status, int32_t defer_copy_back) {
   if (!ctx) return CNGP_ERR_INVALID;
   if (!p || !A || !panel || !winv || !logdet || !status || k < 0 || k >= p->n_blockcols)
     return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_factor_panel: bad argument");
@@ -530,7 +560,8 @@ extern "C" int cngp_large_factor_panel(cngp_ctx* ctx, const cngp_large_plan* p, 
   cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
   large_gemm_kernel<<<dim3((unsigned)(RB - rb0), LG_BT / LG_BLK), LG_THREADS, LG_SMEM, s>>>(g);
   cngp_ctx_end(ctx);
-  // 4. the panel is this block column of L: copy it back under the diagonal block
+  // 4. the panel is this block column of L: copy it back under the diagonal block (or leave that to cngp_large_copy_back)
+  if (!defer_copy_back)
   LCU(ctx, cudaMemcpy2DAsync(Acol + r0 * 64, cstride * 8, panel, pstride * 8, (size_t)(p->row_tiles - r0) * 512, LG_BT,
                              cudaMemcpyDeviceToDevice, s));
   LCU(ctx, cudaGetLastError());
@@ -605,7 +636,7 @@ extern "C" int cngp_large_backsolve_step(cngp_ctx* ctx, const cngp_large_plan* p
   large_back_partial_kernel<<<dim3(LG_BT, BACK_CHUNKS), 256, 0, s>>>(Acol, p->row_tiles, (j + 1) * LG_BT, NT, alpha, partial);
   cngp_ctx_end(ctx);
   cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
-  large_back_finish_kernel<<<1, LG_NB, 0, s>>>(winv + l * LG_BT * LG_BT * 64, z + j * LG_NB, partial, alpha + j * LG_NB);
+  large_back_finish_kernel<<<1, 4 * LG_NB, 0, s>>>(winv + l * LG_BT * LG_BT * 64, z + j * LG_NB, partial, alpha + j * LG_NB);
   cngp_ctx_end(ctx);
   LCU(ctx, cudaGetLastError());
   return CNGP_OK;

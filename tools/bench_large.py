@@ -30,6 +30,7 @@ def run(ctx, N, reps, rank, world, lookahead=True):
     x, y = syn.slip_windows(5, 1, N)
     win = large.LargeWindow(ctx, kname, th, x[0], y[0], rank=rank, world=world)
     times = []
+    host_ms = []
     out = None
     for it in range(reps + 1):
         torch.cuda.synchronize()
@@ -38,7 +39,8 @@ def run(ctx, N, reps, rank, world, lookahead=True):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.set_profiling(it == reps)
         e0.record()
-        out = large.chol_large_distributed(win, rank, world, want_alpha=True, lookahead=lookahead)
+        out = large.chol_large_distributed(win, rank, world, want_alpha=True, lookahead=lookahead,
+                                           profile=(it == reps and bool(os.environ.get("CNGP_LARGE_PHASES"))))
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -46,6 +48,7 @@ def run(ctx, N, reps, rank, world, lookahead=True):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if it > 0:
             times.append(float(t[0]))
+            host_ms.append(out.get("host_enqueue_ms"))
     prof_ms, prof_n = ctx.profile_read(4)
     ctx.set_profiling(False)
     r = ctx.large_matvec(kname, th, win.x, out["alpha"].contiguous())
@@ -55,7 +58,9 @@ def run(ctx, N, reps, rank, world, lookahead=True):
     return {"N": N, "n_gpus": world, "lookahead": lookahead, "ms": times, "best_ms": best,
             "tflops_n3_over_3": N ** 3 / 3.0 / (best * 1e-3) * 1e-12, "lml": out["lml"],
             "logdet": out["logdet"], "quad": out["quad"], "residual": res,
-            "rank0_kernel_ms_last_rep": prof_ms, "rank0_launches_last_rep": prof_n}
+            "rank0_kernel_ms_last_rep": prof_ms, "rank0_launches_last_rep": prof_n,
+            "host_enqueue_ms_per_rep": host_ms,
+            "phase_ms_rank": {"rank": rank, **(out.get("phase_ms") or {})}}
 
 
 def main():
