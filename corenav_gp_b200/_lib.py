@@ -91,6 +91,7 @@ SIGNATURES = {
     "cngp_large_factor_panel": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_dp, c_dp, c_ip]),
     "cngp_large_factor_panel_ex": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_dp, c_dp, c_ip, c_i32]),
     "cngp_large_copy_back": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp]),
+    "cngp_large_update_part": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_i64, c_i64, c_i32]),
     "cngp_large_update": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_i64, c_i64]),
     "cngp_large_reduce": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_dp, c_ip, c_dp, c_dp]),
     "cngp_large_backsolve_step": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_dp, c_i64, c_dp, c_dp]),

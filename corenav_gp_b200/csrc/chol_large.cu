@@ -509,8 +509,9 @@ extern "C" int cngp_large_copy_back(cngp_ctx* ctx, const cngp_large_plan* p, dou
 }
 
 extern "C" int cngp_large_factor_panel_ex(cngp_ctx* ctx, const cngp_large_plan* p, double* A, int64_t k, double* panel,
-                                          double* winv, double* logdet, int32_t* status, int32_t defer_copy_back) {
+                                          double* winv, double* logdet, int32_t* status, int32_t flags) {
   if (!ctx) return CNGP_ERR_INVALID;
+  const bool defer_copy_back = flags & CNGP_LARGE_DEFER_COPY, do_diag = !(flags & CNGP_LARGE_PANEL_ONLY), do_panel = !(flags & CNGP_LARGE_DIAG_ONLY);
   if (!p || !A || !panel || !winv || !logdet || !status || k < 0 || k >= p->n_blockcols)
     return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_factor_panel: bad argument");
   if (k % p->world != p->rank) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_factor_panel: not the owner of this block column");
@@ -526,6 +527,7 @@ extern "C" int cngp_large_factor_panel_ex(cngp_ctx* ctx, const cngp_large_plan* 
   if (!Lpack || !WT || !z33) return cngp_set_error(ctx, CNGP_ERR_NOMEM, "large_factor_panel: scratch");
   double* Wk = winv + l * LG_BT * LG_BT * 64;
 
+  if (do_diag) {
   // 1. diagonal block: tile Cholesky in shared memory (diagonal tiles come out inverted)
   FitArgs fa;
   memset(&fa, 0, sizeof fa);
@@ -544,6 +546,8 @@ extern "C" int cngp_large_factor_panel_ex(cngp_ctx* ctx, const cngp_large_plan* 
   cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
   large_trinv_kernel<<<1, TRI_WARPS * 32, 0, s>>>(Lpack, WT, Wk);
   cngp_ctx_end(ctx);
+  }
+  if (!do_panel) { LCU(ctx, cudaGetLastError()); return CNGP_OK; }
   // 3. panel = (rows below the diagonal block) inv(L_kk)^T
   const int RB = (int)(p->row_tiles / LG_BLK);
   const int rb0 = (int)((rdiag + LG_BT) / LG_BLK);
@@ -570,6 +574,13 @@ extern "C" int cngp_large_factor_panel_ex(cngp_ctx* ctx, const cngp_large_plan* 
 
 extern "C" int cngp_large_update(cngp_ctx* ctx, const cngp_large_plan* p, double* A, int64_t k, const double* panel,
                                  int64_t c_lo, int64_t c_hi) {
+  return cngp_large_update_part(ctx, p, A, k, panel, c_lo, c_hi, CNGP_LARGE_ROWS_ALL);
+}
+
+// rows: CNGP_LARGE_ROWS_ALL, or - for ONE block column - only its diagonal block (so that the block can be factored while
+// the rows below are still being updated on another stream) / only the rows below it.
+extern "C" int cngp_large_update_part(cngp_ctx* ctx, const cngp_large_plan* p, double* A, int64_t k, const double* panel,
+                                      int64_t c_lo, int64_t c_hi, int32_t rows) {
   if (!ctx) return CNGP_ERR_INVALID;
   if (!p || !A || !panel || k < 0 || k >= p->n_blockcols) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_update: bad argument");
   c_lo = std::max<int64_t>(c_lo, k + 1);
@@ -592,11 +603,20 @@ extern "C" int cngp_large_update(cngp_ctx* ctx, const cngp_large_plan* p, double
   g.mode = 1; g.rb0 = rb0; g.world = p->world; g.rank = p->rank;
   LCU(ctx, cudaFuncSetAttribute(large_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_SMEM));
   const long long ncb = (l_hi - l_lo) * (LG_BT / LG_BLK);
+  int rb_first = rb0, rb_count = RB - rb0;
+  if (rows != CNGP_LARGE_ROWS_ALL) {
+    if (l_hi - l_lo != 1) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_update_part: a row part needs exactly one block column");
+    const int diag_blocks = LG_BT / LG_BLK;
+    if (rows == CNGP_LARGE_ROWS_DIAG) rb_count = diag_blocks;
+    else { rb_first = rb0 + diag_blocks; rb_count = RB - rb_first; }
+    if (rb_count <= 0) return CNGP_OK;
+    g.rb0 = rb_first;
+  }
   for (long long y0 = 0; y0 < ncb; y0 += 65535) {
     g.lcb0 = (int)(l_lo * (LG_BT / LG_BLK) + y0);
     const unsigned ny = (unsigned)std::min<long long>(65535, ncb - y0);
     cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
-    large_gemm_kernel<<<dim3((unsigned)(RB - rb0), ny), LG_THREADS, LG_SMEM, s>>>(g);
+    large_gemm_kernel<<<dim3((unsigned)rb_count, ny), LG_THREADS, LG_SMEM, s>>>(g);
     cngp_ctx_end(ctx);
   }
   LCU(ctx, cudaGetLastError());

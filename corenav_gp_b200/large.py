@@ -71,6 +71,7 @@ class LargeWindow:
         self.A = torch.empty(max(1, p.local_doubles), **f64)
         self.panels = [torch.zeros(p.panel_doubles, **f64) for _ in range(self.N_PANELS)]
         self.chain_stream = torch.cuda.Stream(device=dev, priority=-1)   # the serial panel chain runs here
+        self.side_stream = torch.cuda.Stream(device=dev, priority=-1)    # ... and the rows below the block being factored
         self.winv = torch.zeros(max(1, p.winv_doubles), **f64)
         self.logdet = torch.zeros(p.n_blockcols, **f64)
         self.status = torch.zeros(p.n_blockcols, dtype=torch.int32, device=dev)
@@ -99,13 +100,22 @@ class LargeWindow:
                                                self.x.data_ptr(), self.y.data_ptr(), self.A.data_ptr()),
                   "cngp_large_assemble")
 
-    def factor_panel(self, k: int, defer_copy_back: bool = False):
+    DEFER_COPY, DIAG_ONLY, PANEL_ONLY = 1, 2, 4          # cngp.h CNGP_LARGE_*
+    ROWS_ALL, ROWS_DIAG, ROWS_BELOW = 0, 1, 2
+
+    def factor_panel(self, k: int, flags: int = 0):
         self._bind()
         self._chk(self.lib.cngp_large_factor_panel_ex(self.ctx.h, C.byref(self.plan), self.A.data_ptr(), k,
                                                       self.panels[k % self.N_PANELS].data_ptr(), self.winv.data_ptr(),
-                                                      self.logdet.data_ptr(), self.status.data_ptr(),
-                                                      int(defer_copy_back)),
+                                                      self.logdet.data_ptr(), self.status.data_ptr(), int(flags)),
                   "cngp_large_factor_panel")
+
+    def update_part(self, k: int, c: int, rows: int):
+        """Update block column c with panel k: its diagonal block only / only the rows below it."""
+        self._bind()
+        self._chk(self.lib.cngp_large_update_part(self.ctx.h, C.byref(self.plan), self.A.data_ptr(), k,
+                                                  self.panels[k % self.N_PANELS].data_ptr(), c, c + 1, rows),
+                  "cngp_large_update_part")
 
     def copy_back(self, k: int):
         """Store panel k as block column k of L (deferred step of factor_panel; needed by the backward sweep only)."""
@@ -234,6 +244,7 @@ def _factor_two_streams(engine, rank, world, coll, nblk, chain, pt):
                      owner: update column k+1 with panel k, factor; everybody: broadcast panel k+1 into the third buffer.
     Each block column still receives its updates in increasing panel order, so the results are the same bits."""
     main = torch.cuda.current_stream()
+    side = engine.side_stream
     pt.mark("assemble")
     engine.assemble()
     if rank == 0 % world:
@@ -253,8 +264,19 @@ def _factor_two_streams(engine, rank, world, coll, nblk, chain, pt):
                 if k - 2 in buffer_free:
                     chain.wait_event(buffer_free.pop(k - 2))     # panel k+1 goes where panel k-2 was
                 if nxt % world == rank:
-                    engine.update(k, nxt, nxt + 1)
-                    engine.factor_panel(nxt, defer_copy_back=True)
+                    # diagonal block first, then its factorisation + inversion (two single-CTA kernels, 165 us) WHILE the
+                    # rows below are brought up to date on the side stream; the panel GEMM needs both
+                    engine.update_part(k, nxt, engine.ROWS_DIAG)
+                    fork = torch.cuda.Event()
+                    fork.record(chain)
+                    with torch.cuda.stream(side):
+                        side.wait_event(fork)
+                        engine.update_part(k, nxt, engine.ROWS_BELOW)
+                        join = torch.cuda.Event()
+                        join.record(side)
+                    engine.factor_panel(nxt, engine.DIAG_ONLY)
+                    chain.wait_event(join)
+                    engine.factor_panel(nxt, engine.PANEL_ONLY | engine.DEFER_COPY)
                 nxt_pending = coll.broadcast_async(engine.panel_payload(nxt), src=nxt % world)
             pt.mark("trailing_update")
             if k > 0 and k % world == rank:

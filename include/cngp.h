@@ -300,11 +300,24 @@ int cngp_large_assemble(cngp_ctx* ctx, const cngp_large_plan* plan, const cngp_k
  * rt >= r0) is at panel[(kt R + rt - r0) 64], so the first (NB/8) R 64 doubles are what the other ranks need.  logdet[k] = log det of the diagonal block; status[k] = 0 or -(failing pivot, 1-based in block). */
 int cngp_large_factor_panel(cngp_ctx* ctx, const cngp_large_plan* plan, double* A, int64_t k, double* panel,
                             double* winv, double* logdet, int32_t* status);
-/* The same with step 4 (copying the panel back under the diagonal block of A) optionally left to cngp_large_copy_back,
- * which the two-stream driver issues off the panel chain (nothing before the backward sweep reads the copy). */
+/* The same in pieces, for the two-stream driver (flags, OR-ed):
+ *   CNGP_LARGE_DEFER_COPY  step 4 (copying the panel back under the diagonal block of A) is left to cngp_large_copy_back,
+ *                          issued off the panel chain (nothing before the backward sweep reads the copy);
+ *   CNGP_LARGE_DIAG_ONLY   factor and invert the diagonal block only;   CNGP_LARGE_PANEL_ONLY   form the panel only - so
+ *                          that the rows below the diagonal block can still be updated (cngp_large_update_part) on another
+ *                          stream while the block is factored. */
+#define CNGP_LARGE_DEFER_COPY 1
+#define CNGP_LARGE_DIAG_ONLY 2
+#define CNGP_LARGE_PANEL_ONLY 4
+#define CNGP_LARGE_ROWS_ALL 0
+#define CNGP_LARGE_ROWS_DIAG 1
+#define CNGP_LARGE_ROWS_BELOW 2
 int cngp_large_factor_panel_ex(cngp_ctx* ctx, const cngp_large_plan* plan, double* A, int64_t k, double* panel,
-                            double* winv, double* logdet, int32_t* status, int32_t defer_copy_back);
+                            double* winv, double* logdet, int32_t* status, int32_t flags);
 int cngp_large_copy_back(cngp_ctx* ctx, const cngp_large_plan* p, double* A, int64_t k, const double* panel);
+/* cngp_large_update restricted, for ONE block column, to its diagonal block or to the rows below it. */
+int cngp_large_update_part(cngp_ctx* ctx, const cngp_large_plan* plan, double* A, int64_t k, const double* panel,
+                           int64_t c_lo, int64_t c_hi, int32_t rows);
 /* Every rank: A(:, c) -= panel panel(c)^T for its block columns c in [max(c_lo, k+1), c_hi). */
 int cngp_large_update(cngp_ctx* ctx, const cngp_large_plan* plan, double* A, int64_t k, const double* panel,
                       int64_t c_lo, int64_t c_hi);
