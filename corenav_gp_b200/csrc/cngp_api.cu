@@ -755,6 +755,7 @@ int cngp_lml_grad_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* t
       ga.x = d_x; ga.N = N; ga.nt = nt; ga.n_windows = (int)B; ga.problem0 = p0;
       ga.L = Lbuf; ga.W = Wbuf; ga.z = zbuf; ga.alpha = abuf; ga.status = d_status; ga.grad = d_grad;
       ga.skip = skip;
+      ga.lag_ok = fa.lag_ok;
       ctx->begin(CNGP_PROF_GRAD);
       if (nt <= GRAD_SMEM_NT) {
         const size_t gsm = grad_smem_bytes(nt);

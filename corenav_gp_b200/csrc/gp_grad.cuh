@@ -38,6 +38,7 @@ struct GradArgs {
   const int* status;       // [n_problems]
   double* grad;            // [n_problems][P]
   const int* skip;         // [n_problems] or null: problems with skip[p] != 0 are left untouched
+  int lag_ok;              // the expression is stationary (host check): the uniform-stamp contraction may be used
 };
 
 // tile^T in the lane layout: lane (r,q) gets T[2q][r], T[2q+1][r]
@@ -61,6 +62,11 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32) gp_grad_kernel(const GradArgs
   __shared__ double gred[GRAD_WARPS][CNGP_MAX_PARAMS + 1];
   __shared__ int leaf_t0[CNGP_MAX_LEAVES], leaf_t1[CNGP_MAX_LEAVES];   // bounds of the product term a leaf belongs to
   __shared__ GradConst gcs[CNGP_MAX_LEAVES];
+  // uniform mode: dL_dK summed along the diagonals of Ky - per tile diagonal D and in-tile diagonal delta = r - c (lag =
+  // 8 D + delta); every (D, delta) cell has exactly one writer, so the sums do not depend on scheduling (no atomics)
+  __shared__ double sD[CNGP_MAX_N / 8 + 1][16];
+  __shared__ __align__(16) double wst[GRAD_WARPS][64];
+  __shared__ double sdiag;
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int r = lane >> 2, q = lane & 3;
@@ -87,6 +93,13 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32) gp_grad_kernel(const GradArgs
     if (tid < P) a.grad[p * P + tid] = __longlong_as_double(0x7ff8000000000000LL);
     return;
   }
+  // stamps x_i = x_0 + i exactly (integers below 2^26, so that the expanded-form r^2 is exact) and a stationary expression
+  int uni = a.lag_ok;
+  for (int i = tid; i < N; i += GRAD_THREADS) {
+    const double v = a.x[(long long)win * N + i], v0 = a.x[(long long)win * N];
+    uni &= (v == v0 + (double)i) && (v0 == rint(v0)) && (fabs(v) < 67108864.0);
+  }
+  const bool uniform = __syncthreads_and(uni) != 0;
   if (SMEM) {
     const int nd = tiles_in_lower(nt) * 32;     // double2 elements of the factor
     const double2* src = reinterpret_cast<const double2*>(Lp);
@@ -143,6 +156,109 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32) gp_grad_kernel(const GradArgs
 #pragma unroll
   for (int i = 0; i < GRAD_FAST_LEAVES; ++i) gl[i][0] = gl[i][1] = gl[i][2] = 0.0;
   const bool few_leaves = a.kp.n_leaves <= GRAD_FAST_LEAVES;
+  // one entry of dL_dK (weight wgt, mirrored entries included) against dK/dtheta at (xa, xb)
+  auto contract = [&](const double wgt, const double xa, const double xb, const double r2, const bool same) {
+    if (few_leaves) {
+      // Expressions of up to GRAD_FAST_LEAVES leaves (every family of the Kernel Selection study): one accumulator
+      // triple per leaf under a compile-time index - no scan over the CNGP_MAX_PARAMS parameter slots per entry.
+#pragma unroll
+      for (int ul = 0; ul < GRAD_FAST_LEAVES; ++ul) {
+        if (ul < a.kp.n_leaves) {
+          const int u0 = leaf_t0[ul], u1 = leaf_t1[ul];
+          double others = 1.0, dv[3];
+          for (int u2 = u0; u2 < u1; ++u2)
+            if (u2 != ul)
+              others *= leaf_value_grad_c<true>(a.kp.leaf_type[u2], thv + a.kp.leaf_param[u2], gcs[u2], xa, xb, r2, same, dv);
+          leaf_value_grad_c<true>(a.kp.leaf_type[ul], thv + a.kp.leaf_param[ul], gcs[ul], xa, xb, r2, same, dv);
+          const double ww = wgt * others;
+          gl[ul][0] += ww * dv[0]; gl[ul][1] += ww * dv[1]; gl[ul][2] += ww * dv[2];
+        }
+      }
+    } else {
+      for (int tt = 0; tt < a.kp.n_terms; ++tt) {
+        const int u0 = a.kp.term_start[tt], u1 = a.kp.term_start[tt + 1];
+        for (int u = u0; u < u1; ++u) {
+          double others = 1.0, dv[3];
+          for (int u2 = u0; u2 < u1; ++u2)
+            if (u2 != u)
+              others *= leaf_value_grad<true>(a.kp.leaf_type[u2], thv + a.kp.leaf_param[u2], xa, xb, r2, same, dv);
+          leaf_value_grad<true>(a.kp.leaf_type[u], thv + a.kp.leaf_param[u], xa, xb, r2, same, dv);
+          const int np = leaf_nparams(a.kp.leaf_type[u]);
+          const int po = a.kp.leaf_param[u];
+          const double ww = wgt * others;
+#pragma unroll
+          for (int i = 0; i < CNGP_MAX_PARAMS; ++i) {
+            const int jj = i - po;
+            if (jj >= 0 && jj < np) g[i] += ww * (jj == 0 ? dv[0] : (jj == 1 ? dv[1] : dv[2]));
+          }
+        }
+      }
+    }
+  };
+  // Uniform mode: stationary expression on stamps x_i = x_0 + i (the reference's update counts).  Then every entry on one
+  // diagonal of Ky has the same lag, so dL_dK is first summed along diagonals - tiles of one TILE diagonal D = ta - tb are
+  // added elementwise in registers (entries at the same place of those tiles share their lag 8 D + r - c), flushed once
+  // per diagonal into N shared-memory bins - and dK/dtheta is evaluated once per LAG (N evaluations instead of N(N+1)/2
+  // per leaf).  Tile diagonals are dealt to the warps in pairs (D, nt-1-D): nt + 1 tiles each, perfectly balanced.
+  if (uniform) {
+    double sd = 0.0;
+    for (int pr = w; 2 * pr < nt; pr += GRAD_WARPS) {
+      for (int half = 0; half < 2; ++half) {
+        const int D = half ? nt - 1 - pr : pr;
+        if (half && D == pr) break;
+        tile2 acc{0.0, 0.0};
+        const double wsym = D == 0 ? 0.5 : 1.0;
+        for (int tb = 0; tb + D < nt; ++tb) {
+          const int ta = tb + D;
+          const double* pa = Wp + (long long)tile_index(ta, ta, nt) * 64;     // W(m, ta), m = ta ...: consecutive tiles
+          const double* pb = Wp + (long long)tile_index(ta, tb, nt) * 64;     // W(m, tb), m = ta ...
+          tile2 G0{0.0, 0.0}, G1{0.0, 0.0};
+          int m = ta;
+          for (; m + 1 < nt; m += 2) {
+            tile_mma(G0, tile_load(pa, lane), tile_load(pb, lane));
+            tile_mma(G1, tile_load(pa + 64, lane), tile_load(pb + 64, lane));
+            pa += 128; pb += 128;
+          }
+          if (m < nt) tile_mma(G0, tile_load(pa, lane), tile_load(pb, lane));
+          const int row = 8 * ta + r, c0 = 8 * tb + 2 * q;
+          double w0 = (row < N && c0 < N) ? wsym * (al[row] * al[c0] - (G0.a + G1.a)) : 0.0;
+          double w1 = (row < N && c0 + 1 < N) ? wsym * (al[row] * al[c0 + 1] - (G0.b + G1.b)) : 0.0;
+          if (D == 0) {      // the true diagonal goes to its own bin (White, noise)
+            if (row == c0) { sd += w0; w0 = 0.0; }
+            if (row == c0 + 1) { sd += w1; w1 = 0.0; }
+          }
+          acc.a += w0; acc.b += w1;
+        }
+        // the 64 sums of this tile diagonal -> 15 in-tile diagonals, each summed by one lane in a fixed order
+        tile_store(wst[w], lane, acc);
+        __syncwarp();
+        if (lane < 15) {
+          const int dl = lane - 7;
+          double ssum = 0.0;
+          for (int rr = dl > 0 ? dl : 0; rr < (dl < 0 ? 8 + dl : 8); ++rr) ssum += wst[w][rr * 8 + rr - dl];
+          sD[D][lane] = ssum;
+        }
+        __syncwarp();
+      }
+    }
+    for (int o = 16; o; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+    if (w == 0 && lane == 0) sdiag = sd;             // tile diagonal 0 belongs to warp 0 alone
+    __syncthreads();
+    if (tid == 0) g[CNGP_MAX_PARAMS] += sdiag;       // noise: trace(dL_dK)
+    for (int t = tid; t <= N; t += GRAD_THREADS) {   // item N is the true diagonal (one call site for the contraction)
+      const bool dg = t == N;
+      double wl = sdiag;
+      if (!dg) {       // lag t = 8 D + delta: at most two tile diagonals carry it (three cells on tile diagonal 0)
+        const int D = t >> 3, d8 = t & 7;
+        wl = 0.0;
+        if (D == 0) wl = sD[0][7 + d8] + (d8 ? sD[0][7 - d8] : 0.0);
+        else if (D < nt) wl = sD[D][7 + d8];
+        if (d8 && D + 1 < nt) wl += sD[D + 1][d8 - 1];
+      }
+      const double lagv = dg ? 0.0 : (double)t;
+      if (wl != 0.0) contract(wl, lagv, 0.0, lagv * lagv, dg);
+    }
+  } else {
   const int n_tiles = tiles_in_lower(nt);
   for (int t = w; t < n_tiles; t += GRAD_WARPS) {
     // t -> (ta >= tb) by rows of the lower triangle
@@ -174,44 +290,10 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32) gp_grad_kernel(const GradArgs
         double r2 = r2_expanded(xa, xb);
         if (same) r2 = 0.0;
         if (same) g[CNGP_MAX_PARAMS] += wgt;  // noise: trace(dL_dK)
-        if (few_leaves) {
-          // Expressions of up to GRAD_FAST_LEAVES leaves (every family of the Kernel Selection study): one accumulator
-          // triple per leaf under a compile-time index - no scan over the CNGP_MAX_PARAMS parameter slots per entry.
-#pragma unroll
-          for (int ul = 0; ul < GRAD_FAST_LEAVES; ++ul) {
-            if (ul < a.kp.n_leaves) {
-              const int u0 = leaf_t0[ul], u1 = leaf_t1[ul];
-              double others = 1.0, dv[3];
-              for (int u2 = u0; u2 < u1; ++u2)
-                if (u2 != ul)
-                  others *= leaf_value_grad_c<true>(a.kp.leaf_type[u2], thv + a.kp.leaf_param[u2], gcs[u2], xa, xb, r2, same, dv);
-              leaf_value_grad_c<true>(a.kp.leaf_type[ul], thv + a.kp.leaf_param[ul], gcs[ul], xa, xb, r2, same, dv);
-              const double ww = wgt * others;
-              gl[ul][0] += ww * dv[0]; gl[ul][1] += ww * dv[1]; gl[ul][2] += ww * dv[2];
-            }
-          }
-        } else {
-          for (int tt = 0; tt < a.kp.n_terms; ++tt) {
-            const int u0 = a.kp.term_start[tt], u1 = a.kp.term_start[tt + 1];
-            for (int u = u0; u < u1; ++u) {
-              double others = 1.0, dv[3];
-              for (int u2 = u0; u2 < u1; ++u2)
-                if (u2 != u)
-                  others *= leaf_value_grad<true>(a.kp.leaf_type[u2], thv + a.kp.leaf_param[u2], xa, xb, r2, same, dv);
-              leaf_value_grad<true>(a.kp.leaf_type[u], thv + a.kp.leaf_param[u], xa, xb, r2, same, dv);
-              const int np = leaf_nparams(a.kp.leaf_type[u]);
-              const int po = a.kp.leaf_param[u];
-              const double ww = wgt * others;
-#pragma unroll
-              for (int i = 0; i < CNGP_MAX_PARAMS; ++i) {
-                const int jj = i - po;
-                if (jj >= 0 && jj < np) g[i] += ww * (jj == 0 ? dv[0] : (jj == 1 ? dv[1] : dv[2]));
-              }
-            }
-          }
-        }
+        contract(wgt, xa, xb, r2, same);
       }
     }
+  }
   }
   if (few_leaves) {   // hand the per-leaf sums to their parameter slots
 #pragma unroll
