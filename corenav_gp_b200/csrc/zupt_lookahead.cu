@@ -190,6 +190,7 @@ __device__ __forceinline__ void ut_R(double mean, double sigma, const cngp_stop_
 struct ObsBound {
   double habs, coslat0, tilt0;
   bool usable;
+  double c1, c2, c3, t2;   // square-root-free form of the same bound (obs_cannot_trigger_sq)
 };
 __device__ __forceinline__ ObsBound obs_prepare(double lat, double lon, double h, const cngp_stop_config& c) {
   ObsBound o;
@@ -197,7 +198,20 @@ __device__ __forceinline__ ObsBound obs_prepare(double lat, double lon, double h
   o.coslat0 = fabs(cos(lat));
   o.tilt0 = fabs(lat - c.init_llh[0]) + fabs(lon - c.init_llh[1]);
   o.usable = fabs(lat) < 1.4;       // the closed form of gp_predictor.cpp:150-160 is the ellipsoid map away from the poles
+  // The same bound without square roots, from u = |P66|, v = |P77|, hh = |P88| (dl = 3 sqrt u ...), valid while
+  // dl, dm < 1e-3 rad and dh < 1e3 m:  bound <= 1.0011 sqrt(X) + y,  X = Rb1^2 9 (u + (coslat0 + 1e-3)^2 v),
+  // y = dh tilt1, and (s + y)^2 <= (1 + 1e-3) s^2 + 1001 y^2.  It is ~0.2 % more conservative than the form above (a few
+  // more exact evaluations close to the threshold) and takes three square roots off every step of the look-ahead.
+  const double Rb1 = 6.4e6 + o.habs + 1.0e3, tilt1 = fmin(1.0, o.tilt0 + 2.0e-3);
+  o.c1 = 1.001 * 1.0011 * 1.0011 * 9.0 * Rb1 * Rb1;
+  o.c2 = (o.coslat0 + 1.0e-3) * (o.coslat0 + 1.0e-3);
+  o.c3 = 1001.0 * 9.0 * tilt1 * tilt1;
+  o.t2 = c.thresh > 1.0e-3 ? (c.thresh - 1.0e-6) * (c.thresh - 1.0e-6) : -1.0;
   return o;
+}
+__device__ __forceinline__ bool obs_cannot_trigger_sq(const ObsBound& o, double u, double v, double hh) {
+  return o.usable && (9.0 * u < 1.0e-6) && (9.0 * v < 1.0e-6) && (9.0 * hh < 1.0e6) &&
+         (o.c1 * (u + o.c2 * v) + o.c3 * hh < o.t2);                                   // NaN compares false: exact path
 }
 __device__ __forceinline__ bool obs_cannot_trigger(const ObsBound& o, double dl, double dm, double dh, double thresh) {
   const double Rb = 6.4e6 + o.habs + dh;
@@ -497,8 +511,9 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 2) zupt_lookahead_tc_kernel(con
       ++i_upd;
     }
     // ---- error observer ----
-    const double dl3 = 3.0 * sqrt(fabs(Ps[6 * TC_LD + 6])), dm3 = 3.0 * sqrt(fabs(Ps[7 * TC_LD + 7])),
-                 dh3 = 3.0 * sqrt(fabs(Ps[8 * TC_LD + 8]));
+    const double p66 = fabs(Ps[6 * TC_LD + 6]), p77 = fabs(Ps[7 * TC_LD + 7]), p88 = fabs(Ps[8 * TC_LD + 8]);
+    if (slip_i + 1 < nsteps && obs_cannot_trigger_sq(ob, p66, p77, p88)) continue;      // no square roots on this path
+    const double dl3 = 3.0 * sqrt(p66), dm3 = 3.0 * sqrt(p77), dh3 = 3.0 * sqrt(p88);
     if (slip_i + 1 < nsteps && obs_cannot_trigger(ob, dl3, dm3, dh3, cfg.thresh)) continue;
     const double lat3 = lat + dl3;
     const double lon3 = lon + dm3;
