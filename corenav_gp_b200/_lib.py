@@ -41,10 +41,11 @@ class SlipConfig(C.Structure):   # cngp_slip_config
 class LargePlan(C.Structure):
     _fields_ = [("N", c_i64), ("n_pad", c_i64), ("world", c_i32), ("rank", c_i32), ("row_tiles", c_i64),
                 ("n_blockcols", c_i64), ("n_local_blockcols", c_i64), ("local_doubles", c_i64),
-                ("panel_doubles", c_i64), ("winv_doubles", c_i64)]
+                ("panel_doubles", c_i64), ("winv_doubles", c_i64), ("chunk_blocks", c_i64)]
 
 
 LARGE_NB = 256
+LARGE_MAX_CHUNKS = 16
 
 # every symbol include/cngp.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -89,9 +90,14 @@ SIGNATURES = {
     "cngp_large_make_plan": (C.c_int, [c_i64, c_i32, c_i32, C.POINTER(LargePlan)]),
     "cngp_large_assemble": (C.c_int, [c_vp, C.POINTER(LargePlan), C.POINTER(Kernel), c_dp, c_dp, c_dp, c_dp]),
     "cngp_large_factor_panel": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_dp, c_dp, c_ip]),
-    "cngp_large_factor_panel_ex": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_dp, c_dp, c_ip, c_i32]),
+    "cngp_large_factor_panel_ex": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_dp, c_dp, c_ip, c_i32, c_i32]),
+    "cngp_large_panel_chunks": (C.c_int, [C.POINTER(LargePlan), c_i64, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i64)]),
+    "cngp_large_backsolve_finish": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_dp, c_dp]),
+    "cngp_large_backsolve_apply": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_i64, c_dp, c_dp]),
+    "cngp_large_group_finish": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_i64, c_dp, c_dp, c_dp]),
+    "cngp_large_group_apply": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_i64, c_i64, c_dp, c_dp]),
     "cngp_large_copy_back": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp]),
-    "cngp_large_update_part": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_i64, c_i64, c_i32]),
+    "cngp_large_update_part": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_i64, c_i64, c_i32, c_i32]),
     "cngp_large_update": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_i64, c_i64]),
     "cngp_large_reduce": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_dp, c_ip, c_dp, c_dp]),
     "cngp_large_backsolve_step": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_dp, c_i64, c_dp, c_dp]),

@@ -120,63 +120,108 @@ __global__ void __launch_bounds__(ASM_WARPS * 32) large_assemble_kernel(const As
 // inverse of the factored diagonal block: W = L^-1 as 32 x 32 tiles in [k-tile][row-tile] order (the Y operand
 // layout of large_gemm_kernel), from the packed factor gp_fit_kernel writes (diagonal tiles already inverted).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int TRI_WARPS = 16;
 __device__ __forceinline__ tile2 tile_load_transposed(const double* tile, int lane) {
   const int r = lane >> 2, q = lane & 3;
   return tile2{tile[(2 * q) * 8 + r], tile[(2 * q + 1) * 8 + r]};
 }
 
-__global__ void __launch_bounds__(TRI_WARPS * 32) large_trinv_kernel(const double* Lp, double* WT, double* W) {
-  const int nt = LG_BT;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  // WT(i,j) = (L^-1)_ij^T, column by column:  T^T = sum_{k=j}^{i-1} WT(k,j) L(i,k)^T,  WT(i,j) = -T^T inv(L_ii)^T
-  // heavy columns (small j) are paired with light ones on the same warp: columns w and 31 - w
-  for (int pass = 0; pass < 2; ++pass) {
-    const int j = pass == 0 ? w : nt - 1 - w;
-    tile_store(WT + (long long)tile_index(j, j, nt) * 64, lane,
-               tile_load_transposed(Lp + (long long)tile_index(j, j, nt) * 64, lane));
-    __syncwarp();
-    for (int i = j + 1; i < nt; ++i) {
-      tile2 T0{0.0, 0.0}, T1{0.0, 0.0};
-      int k = j;
-      for (; k + 1 < i; k += 2) {
-        tile_mma(T0, tile_load(WT + (long long)tile_index(k, j, nt) * 64, lane),
-                 tile_load(Lp + (long long)tile_index(i, k, nt) * 64, lane));
-        tile_mma(T1, tile_load(WT + (long long)tile_index(k + 1, j, nt) * 64, lane),
-                 tile_load(Lp + (long long)tile_index(i, k + 1, nt) * 64, lane));
-      }
-      if (k < i)
-        tile_mma(T0, tile_load(WT + (long long)tile_index(k, j, nt) * 64, lane),
-                 tile_load(Lp + (long long)tile_index(i, k, nt) * 64, lane));
-      const tile2 nT{-(T0.a + T1.a), -(T0.b + T1.b)};
-      tile2 Wt{0.0, 0.0};
-      tile_mma(Wt, nT, tile_load(Lp + (long long)tile_index(i, i, nt) * 64, lane));
-      tile_store(WT + (long long)tile_index(i, j, nt) * 64, lane, Wt);
-      __syncwarp();
-    }
+// One CTA per tile column j of X = L^-1, one warp per row tile i.  With WT(i,j) = X(i,j)^T:
+//   WT(j,j) = inv(L_jj)^T,   WT(i,j) = -(sum_{k=j}^{i-1} WT(k,j) L(i,k)^T) inv(L_ii)^T.
+// Right-looking inside the column: as soon as WT(k,j) is published (shared memory, double-buffered) every warp i > k
+// adds its term WT(k,j) L(i,k)^T to the sum it keeps in registers, and warp k+1 - whose sum is then complete - finishes
+// and publishes WT(k+1,j).  The dependent chain per step is two tile products and one CTA barrier; the L tiles are
+// prefetched one step ahead.  (Round 1 ran all 32 columns on ONE CTA, two per warp, each step re-reading its column
+// from global memory: 76 us on the serial panel chain of every block column; this is 32 CTAs and a few microseconds.)
+constexpr int TRI_WARPS = LG_BT;
+__global__ void __launch_bounds__(TRI_WARPS * 32) large_trinv_kernel(const double* __restrict__ Lp, double* __restrict__ W) {
+  __shared__ __align__(16) double cur[2][64];
+  constexpr int nt = LG_BT;
+  const int lane = threadIdx.x & 31, i = threadIdx.x >> 5, j = blockIdx.x;
+  const int r = lane >> 2, q = lane & 3;
+  tile2 acc{0.0, 0.0}, mine{0.0, 0.0};
+  if (i == j) {
+    mine = tile_load_transposed(Lp + (long long)tile_index(j, j, nt) * 64, lane);
+    tile_store(cur[0], lane, mine);
+  }
+  tile2 lnext{0.0, 0.0}, linv{0.0, 0.0};
+  if (i > j) {
+    lnext = tile_load(Lp + (long long)tile_index(i, j, nt) * 64, lane);
+    linv = tile_load(Lp + (long long)tile_index(i, i, nt) * 64, lane);
   }
   __syncthreads();
-  // W tile (row tile i, k-tile j) = WT(i,j)^T at W[(j * 32 + i) * 64]; zero above the diagonal
-  for (int idx = w; idx < nt * nt; idx += TRI_WARPS) {
-    const int j = idx / nt, i = idx % nt;
-    tile2 v{0.0, 0.0};
-    if (i >= j) v = tile_load_transposed(WT + (long long)tile_index(i, j, nt) * 64, lane);
-    tile_store(W + (long long)idx * 64, lane, v);
+  for (int k = j; k + 1 < nt; ++k) {
+    if (i > k) {
+      const tile2 lik = lnext;
+      if (k + 1 < i) lnext = tile_load(Lp + (long long)tile_index(i, k + 1, nt) * 64, lane);
+      tile_mma(acc, tile_load(cur[(k - j) & 1], lane), lik);
+      if (i == k + 1) {
+        const tile2 nT{-acc.a, -acc.b};
+        tile_mma(mine, nT, linv);
+        tile_store(cur[(k + 1 - j) & 1], lane, mine);
+      }
+    }
+    __syncthreads();
   }
+  // W tile (row tile i, k-tile j) = X(i,j) = WT(i,j)^T at W[(j * 32 + i) * 64]; zero above the diagonal
+  double* out = W + ((long long)j * nt + i) * 64;
+  out[(2 * q) * 8 + r] = mine.a;          // mine is zero for i < j
+  out[(2 * q + 1) * 8 + r] = mine.b;
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // tile GEMM:  C(rt, ct) (-)= sum_k X(k, rt) Y(k, n)^T
 // ------------------------------------------------------------------------------------------------------------
+// Panel buffer layout.  A panel holds the rows below its diagonal block: row tiles r0 .. row_tiles, 32 k-tiles wide.
+// It is cut into CHUNKS of rows at fixed absolute positions (every `cs` 16-tile row blocks, cs even; cs = 0: one chunk),
+// each chunk stored compactly on its own - [k-tile][row tile of the chunk] - one after the other, so that a chunk is ONE
+// contiguous range: the unit of the broadcast, of the panel GEMM and of the update of the next block column, which the
+// driver pipelines chunk by chunk (large.py).  The chunk of row tile rt and where its tiles are:
+struct PanelGeom {
+  long long r0, row_tiles;
+  int cs;                      // chunk size in 16-tile row blocks, 0 = single chunk
+};
+struct ChunkLoc { long long base, kstride; };   // tile (kt, rt) of the chunk at P + base + kt * kstride + rt * 64
+__host__ __device__ inline int chunk_count_abs(long long row_tiles, int cs) {
+  if (cs <= 0) return 1;
+  const long long rb = row_tiles / LG_BLK;
+  return rb / cs > 1 ? (int)(rb / cs) : 1;             // the last chunk takes the remainder
+}
+__host__ __device__ inline void chunk_rows(const PanelGeom& g, int chunk, long long& lo, long long& hi) {
+  const int n = chunk_count_abs(g.row_tiles, g.cs);
+  if (g.cs <= 0) { lo = g.r0; hi = g.row_tiles; return; }
+  lo = (long long)chunk * g.cs * LG_BLK;
+  hi = chunk == n - 1 ? g.row_tiles : (long long)(chunk + 1) * g.cs * LG_BLK;
+  if (lo < g.r0) lo = g.r0;
+  if (hi < lo) hi = lo;
+}
+__host__ __device__ inline int chunk_of(const PanelGeom& g, long long rt) {
+  if (g.cs <= 0) return 0;
+  const int n = chunk_count_abs(g.row_tiles, g.cs);
+  const long long c = rt / ((long long)g.cs * LG_BLK);
+  return (int)(c < n - 1 ? c : n - 1);
+}
+__host__ __device__ inline ChunkLoc chunk_loc(const PanelGeom& g, long long rt) {
+  long long lo, hi;
+  chunk_rows(g, chunk_of(g, rt), lo, hi);
+  ChunkLoc c;
+  c.kstride = (hi - lo) * 64;
+  c.base = (long long)LG_BT * 64 * (lo - g.r0) - lo * 64;   // every chunk before this one holds 32 k-tiles of its rows
+  return c;
+}
+
 struct GemmArgs {
   const double* X; long long x_kstride;   // X tile (k, rt) at X + k * x_kstride + rt * 64
   const double* Y; long long y_kstride;   // Y tile (k, n)  at Y + k * y_kstride + n * 64
   double* C;       long long c_cstride;   // C tile (rt, ct) at C + ct * c_cstride + rt * 64
-  int mode;       // 0: C = X Y^T, Y lower-triangular inverse block (k-tiles up to the column block's last tile)
-                  // 1: C -= X Y^T over all 32 k-tiles; column blocks are local block-cyclic, lower blocks only
+  int mode;       // 0: C = X Y^T, Y lower-triangular inverse block (k-tiles up to the column block's last tile); C is
+                  //    the panel buffer `panel` in the chunked layout `pg`
+                  // 1: C -= X Y^T over all 32 k-tiles; column blocks are local block-cyclic, lower blocks only; X and Y
+                  //    are both the panel buffer `panel` (layout `pg`)
   int rb0;        // first row block of the launch (units of 16 tiles); blockIdx.x counts from it
   int lcb0;       // mode 1: first local column block (units of 16 tiles); blockIdx.y counts from it
   int world, rank;
+  double* panel;
+  PanelGeom pg;
 };
 
 __global__ void __launch_bounds__(LG_THREADS, 1) large_gemm_kernel(const GemmArgs a) {
@@ -197,6 +242,20 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_gemm_kernel(const GemmArg
     KT = LG_BT;
     if (rt0 < n0) return;                // block strictly above the diagonal
   }
+  // operands: a 16-tile block never straddles two chunks of the panel (chunk boundaries are multiples of 16 tiles)
+  const double *Xb, *Yb;
+  long long xks, yks, ccs;
+  double* Cb;
+  if (a.mode == 0) {
+    const ChunkLoc c = chunk_loc(a.pg, rt0);
+    Xb = a.X; xks = a.x_kstride; Yb = a.Y; yks = a.y_kstride;
+    Cb = a.panel + c.base; ccs = c.kstride;
+  } else {
+    const ChunkLoc cx = chunk_loc(a.pg, rt0), cy = chunk_loc(a.pg, n0);
+    Xb = a.panel + cx.base; xks = cx.kstride;
+    Yb = a.panel + cy.base; yks = cy.kstride;
+    Cb = a.C; ccs = a.c_cstride;
+  }
   const uint32_t full_u32 = smem_u32(&bars[0]), empty_u32 = smem_u32(&bars[LG_STAGES]);
   if (tid == 0) {
     for (int s = 0; s < LG_STAGES; ++s) { mbar_init(full_u32 + 8 * s, 1); mbar_init(empty_u32 + 8 * s, LG_CONSUMERS); }
@@ -213,8 +272,8 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_gemm_kernel(const GemmArg
 #pragma unroll
     for (int kk = 0; kk < LG_KC; ++kk) {
       const long long k = (long long)it * LG_KC + kk;
-      bulk_g2s(dst + kk * LG_SLAB * 8, a.X + k * a.x_kstride + rt0 * 64, LG_SLAB * 8, full_u32 + 8 * s);
-      bulk_g2s(dst + (LG_KC + kk) * LG_SLAB * 8, a.Y + k * a.y_kstride + n0 * 64, LG_SLAB * 8, full_u32 + 8 * s);
+      bulk_g2s(dst + kk * LG_SLAB * 8, Xb + k * xks + rt0 * 64, LG_SLAB * 8, full_u32 + 8 * s);
+      bulk_g2s(dst + (LG_KC + kk) * LG_SLAB * 8, Yb + k * yks + n0 * 64, LG_SLAB * 8, full_u32 + 8 * s);
     }
   };
   if (tid == 0)
@@ -223,13 +282,13 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_gemm_kernel(const GemmArg
   // ---- consumers: warp (wr, wc) owns row tiles wr*8 .. +8 and column tiles wc*4 .. +4 of the block ----
   const int wr = w >> 2, wc = w & 3;
   tile2 acc[8][4];
-  double* cbase = a.C + (ct0 + wc * 4) * a.c_cstride + (rt0 + wr * 8) * 64 + 2 * lane;
+  double* cbase = Cb + (ct0 + wc * 4) * ccs + (rt0 + wr * 8) * 64 + 2 * lane;
   if (a.mode == 1) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const double2 v = *reinterpret_cast<const double2*>(cbase + j * a.c_cstride + i * 64);
+        const double2 v = *reinterpret_cast<const double2*>(cbase + j * ccs + i * 64);
         acc[i][j] = tile2{v.x, v.y};
       }
   } else {
@@ -273,7 +332,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_gemm_kernel(const GemmArg
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      *reinterpret_cast<double2*>(cbase + j * a.c_cstride + i * 64) = make_double2(acc[i][j].a, acc[i][j].b);
+      *reinterpret_cast<double2*>(cbase + j * ccs + i * 64) = make_double2(acc[i][j].a, acc[i][j].b);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -345,13 +404,13 @@ __global__ void __launch_bounds__(256) large_back_partial_kernel(const double* A
 // row segments of 64 (a single thread walking a whole column made this 39 us of pure load latency per block column -
 // 5 ms of the 128-step backward sweep).
 __global__ void __launch_bounds__(4 * LG_NB) large_back_finish_kernel(const double* W, const double* zj, const double* partial,
-                                                                      double* alpha_j) {
+                                                                      int nparts, double* alpha_j) {
   __shared__ double t[LG_NB];
   __shared__ double seg_sum[4][LG_NB];
   const int c = threadIdx.x % LG_NB, seg = threadIdx.x / LG_NB;
   if (seg == 0) {
     double s = zj[c];
-    for (int ch = 0; ch < BACK_CHUNKS; ++ch) s -= partial[ch * LG_NB + c];
+    for (int ch = 0; ch < nparts; ++ch) s -= partial[ch * LG_NB + c];
     t[c] = s;
   }
   __syncthreads();
@@ -363,6 +422,64 @@ __global__ void __launch_bounds__(4 * LG_NB) large_back_finish_kernel(const doub
   seg_sum[seg][c] = acc;
   __syncthreads();
   if (seg == 0) alpha_j[c] = ((seg_sum[0][c] + seg_sum[1][c]) + seg_sum[2][c]) + seg_sum[3][c];
+}
+
+// The backward sweep the other way round ("lazy"): instead of the owner of block column j summing its whole column
+// against alpha when its turn comes (a pass over up to 67 MB on the serial path of every step), every rank adds the
+// contribution of alpha_j to ALL its block columns c < j as soon as alpha_j is known:
+//     s[8 ct + col] += sum_rows L(row in block row j, 8 ct + col) alpha_j[row]
+// so that when column j-1's turn comes its sum is complete after one 256-row slice.  One warp per column tile (32 tiles
+// of 512 B, contiguous); each column tile has one writer and receives its block rows in descending order on every world
+// size, so alpha has the same bits on 1 and on 8 GPUs.
+// one warp: out[0..7] += sum over the 32 row tiles at `col` (consecutive tiles of one column tile) of tile^T alpha
+__device__ __forceinline__ void back_apply_column_tile(const double* col, const double* al, double* out, int lane) {
+  const int r = lane >> 2, q = lane & 3;
+  col += 2 * lane;
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+  for (int t = 0; t < LG_BT; ++t) {
+    const double2 v = *reinterpret_cast<const double2*>(col + t * 64);
+    const double a = al[8 * t + r];
+    s0 = fma(v.x, a, s0);
+    s1 = fma(v.y, a, s1);
+  }
+  for (int o = 4; o < 32; o <<= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if (r == 0) {
+    out[2 * q] += s0;
+    out[2 * q + 1] += s1;
+  }
+}
+
+__global__ void __launch_bounds__(256) large_back_apply_kernel(const double* A, long long row_tiles, long long j,
+                                                               long long n_lct, int world, int rank,
+                                                               const double* alpha_j, double* s) {
+  __shared__ double al[LG_NB];
+  for (int i = threadIdx.x; i < LG_NB; i += blockDim.x) al[i] = alpha_j[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long lct = (long long)blockIdx.x * 8 + w;
+  if (lct >= n_lct) return;
+  const long long c = (lct / LG_BT) * world + rank;
+  back_apply_column_tile(A + (lct * row_tiles + j * LG_BT) * 64, al, s + 8 * (c * LG_BT + lct % LG_BT), lane);
+}
+
+// The same for the blocks of a GROUP of `world` consecutive block columns, read from the replicated band (every rank
+// holds, for every block column c, inv(L_cc) and the blocks L(c + d, c) that lie inside c's group):
+// s_c += L(i, c)^T alpha_i for c in [c_lo, i).  Block (c, d) of the band at band + (((c % world) nl + c / world) G + d) BLK.
+constexpr long long BAND_BLK = (long long)LG_BT * LG_BT * 64;
+__global__ void __launch_bounds__(256) large_group_apply_kernel(const double* band, long long nl, int G, int world,
+                                                                long long i, long long c_lo, const double* alpha_i, double* s) {
+  __shared__ double al[LG_NB];
+  for (int t = threadIdx.x; t < LG_NB; t += blockDim.x) al[t] = alpha_i[t];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long c = c_lo + blockIdx.y;
+  const int ct = blockIdx.x * 8 + w;
+  const double* blk = band + (((c % world) * nl + c / world) * G + (i - c)) * BAND_BLK;
+  back_apply_column_tile(blk + (long long)ct * LG_BT * 64, al, s + 8 * (c * LG_BT + ct), lane);
 }
 
 // r = Ky v with Ky evaluated on the fly; one warp per row
@@ -422,6 +539,14 @@ int cuda_fail(cngp_ctx* ctx, const char* what, cudaError_t e) {
 // scratch slots of the context used here
 enum { SLOT_THETA = 20, SLOT_LPACK = 21, SLOT_WT = 22, SLOT_Z33 = 23, SLOT_PARTIAL = 24 };
 
+inline PanelGeom panel_geom(const cngp_large_plan* p, long long k) {
+  PanelGeom g;
+  g.r0 = (k + 1) * LG_BT;
+  g.row_tiles = p->row_tiles;
+  g.cs = (int)p->chunk_blocks;
+  return g;
+}
+
 inline long long local_index_of(long long c_lo, int world, int rank) {   // smallest l with l*world + rank >= c_lo
   if (c_lo <= rank) return 0;
   return (c_lo - rank + world - 1) / world;
@@ -431,7 +556,7 @@ inline long long local_index_of(long long c_lo, int world, int rank) {   // smal
 
 extern "C" int cngp_large_make_plan(int64_t N, int32_t world, int32_t rank, cngp_large_plan* p) {
   if (!p || N <= 0 || world <= 0 || rank < 0 || rank >= world) return CNGP_ERR_INVALID;
-  memset(p, 0, sizeof *p);
+  memset(p, 0, sizeof *p);     // chunk_blocks = 0: panels in one piece (the caller may set it, see cngp.h)
   p->N = N;
   p->n_pad = (N + LG_NB - 1) / LG_NB * LG_NB;
   p->world = world;
@@ -488,7 +613,7 @@ extern "C" int cngp_large_assemble(cngp_ctx* ctx, const cngp_large_plan* p, cons
 
 extern "C" int cngp_large_factor_panel(cngp_ctx* ctx, const cngp_large_plan* p, double* A, int64_t k, double* panel,
                                        double* winv, double* logdet, int32_t* status) {
-  return cngp_large_factor_panel_ex(ctx, p, A, k, panel, winv, logdet, status, 0);
+  return cngp_large_factor_panel_ex(ctx, p, A, k, panel, winv, logdet, status, 0, -1);
 }
 
 // 4. of cngp_large_factor_panel on its own: the panel is this block column of L - copy it back under the diagonal block.
@@ -500,16 +625,40 @@ extern "C" int cngp_large_copy_back(cngp_ctx* ctx, const cngp_large_plan* p, dou
   LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
   const long long l = k / p->world, cstride = p->row_tiles * 64;
   double* Acol = A + l * LG_BT * cstride;
-  const long long r0 = k * LG_BT + LG_BT;
-  const long long pstride = (p->row_tiles - r0) * 64;
-  if (p->row_tiles - r0 <= 0) return CNGP_OK;
-  LCU(ctx, cudaMemcpy2DAsync(Acol + r0 * 64, cstride * 8, panel, pstride * 8, (size_t)(p->row_tiles - r0) * 512, LG_BT,
-                             cudaMemcpyDeviceToDevice, cngp_ctx_stream(ctx)));
+  const PanelGeom pg = panel_geom(p, k);
+  for (int c = chunk_of(pg, pg.r0); c < chunk_count_abs(pg.row_tiles, pg.cs); ++c) {
+    long long lo, hi;
+    chunk_rows(pg, c, lo, hi);
+    if (hi <= lo) continue;
+    const ChunkLoc loc = chunk_loc(pg, lo);
+    LCU(ctx, cudaMemcpy2DAsync(Acol + lo * 64, cstride * 8, panel + loc.base + lo * 64, loc.kstride * 8, (size_t)(hi - lo) * 512,
+                               LG_BT, cudaMemcpyDeviceToDevice, cngp_ctx_stream(ctx)));
+  }
+  return CNGP_OK;
+}
+
+// Live chunks of panel k: *first = absolute id of the first one, *count = how many, offsets[0 .. count] = where each starts
+// in the panel buffer (doubles; offsets[count] = end of the payload).  offsets must hold CNGP_LARGE_MAX_CHUNKS + 1 entries.
+extern "C" int cngp_large_panel_chunks(const cngp_large_plan* p, int64_t k, int32_t* first, int32_t* count, int64_t* offsets) {
+  if (!p || !first || !count || !offsets || k < 0 || k >= p->n_blockcols) return CNGP_ERR_INVALID;
+  const PanelGeom pg = panel_geom(p, k);
+  const int n = chunk_count_abs(pg.row_tiles, pg.cs);
+  if (n > CNGP_LARGE_MAX_CHUNKS) return CNGP_ERR_INVALID;
+  const int c0 = chunk_of(pg, pg.r0);
+  *first = c0;
+  int m = 0;
+  for (int c = c0; c < n; ++c) {
+    long long lo, hi;
+    chunk_rows(pg, c, lo, hi);
+    offsets[m++] = (long long)LG_BT * 64 * (lo - pg.r0);
+    if (c == n - 1) offsets[m] = (long long)LG_BT * 64 * (hi - pg.r0);
+  }
+  *count = m;
   return CNGP_OK;
 }
 
 extern "C" int cngp_large_factor_panel_ex(cngp_ctx* ctx, const cngp_large_plan* p, double* A, int64_t k, double* panel,
-                                          double* winv, double* logdet, int32_t* status, int32_t flags) {
+                                          double* winv, double* logdet, int32_t* status, int32_t flags, int32_t chunk) {
   if (!ctx) return CNGP_ERR_INVALID;
   const bool defer_copy_back = flags & CNGP_LARGE_DEFER_COPY, do_diag = !(flags & CNGP_LARGE_PANEL_ONLY), do_panel = !(flags & CNGP_LARGE_DIAG_ONLY);
   if (!p || !A || !panel || !winv || !logdet || !status || k < 0 || k >= p->n_blockcols)
@@ -522,9 +671,8 @@ extern "C" int cngp_large_factor_panel_ex(cngp_ctx* ctx, const cngp_large_plan* 
   double* Acol = A + l * LG_BT * cstride;                 // block column k
   const long long rdiag = k * LG_BT;                      // first row tile of the diagonal block
   double* Lpack = (double*)cngp_ctx_buf(ctx, SLOT_LPACK, sizeof(double) * tiles_in_lower(LG_BT) * 64);
-  double* WT = (double*)cngp_ctx_buf(ctx, SLOT_WT, sizeof(double) * tiles_in_lower(LG_BT) * 64);
   double* z33 = (double*)cngp_ctx_buf(ctx, SLOT_Z33, sizeof(double) * (LG_NB + 8));
-  if (!Lpack || !WT || !z33) return cngp_set_error(ctx, CNGP_ERR_NOMEM, "large_factor_panel: scratch");
+  if (!Lpack || !z33) return cngp_set_error(ctx, CNGP_ERR_NOMEM, "large_factor_panel: scratch");
   double* Wk = winv + l * LG_BT * LG_BT * 64;
 
   if (do_diag) {
@@ -544,43 +692,44 @@ extern "C" int cngp_large_factor_panel_ex(cngp_ctx* ctx, const cngp_large_plan* 
   cngp_ctx_end(ctx);
   // 2. inverse of the block factor
   cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
-  large_trinv_kernel<<<1, TRI_WARPS * 32, 0, s>>>(Lpack, WT, Wk);
+  large_trinv_kernel<<<LG_BT, TRI_WARPS * 32, 0, s>>>(Lpack, Wk);
   cngp_ctx_end(ctx);
   }
   if (!do_panel) { LCU(ctx, cudaGetLastError()); return CNGP_OK; }
-  // 3. panel = (rows below the diagonal block) inv(L_kk)^T
-  const int RB = (int)(p->row_tiles / LG_BLK);
-  const int rb0 = (int)((rdiag + LG_BT) / LG_BLK);
-  // the panel buffer is compact: tile (k, rt) at panel + (k * (row_tiles - r0) + rt - r0) * 64 with r0 the first row
-  // tile below the diagonal block, so what has to be broadcast is one contiguous prefix of the buffer
-  const long long r0 = rdiag + LG_BT;
-  const long long pstride = (p->row_tiles - r0) * 64;
-  GemmArgs g;
-  g.X = Acol; g.x_kstride = cstride;
-  g.Y = Wk; g.y_kstride = (long long)LG_BT * 64;
-  g.C = panel - r0 * 64; g.c_cstride = pstride;
-  g.mode = 0; g.rb0 = rb0; g.lcb0 = 0; g.world = p->world; g.rank = p->rank;
-  LCU(ctx, cudaFuncSetAttribute(large_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_SMEM));
-  cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
-  large_gemm_kernel<<<dim3((unsigned)(RB - rb0), LG_BT / LG_BLK), LG_THREADS, LG_SMEM, s>>>(g);
-  cngp_ctx_end(ctx);
-  // 4. the panel is this block column of L: copy it back under the diagonal block (or leave that to cngp_large_copy_back)
-  if (!defer_copy_back)
-  LCU(ctx, cudaMemcpy2DAsync(Acol + r0 * 64, cstride * 8, panel, pstride * 8, (size_t)(p->row_tiles - r0) * 512, LG_BT,
-                             cudaMemcpyDeviceToDevice, s));
+  // 3. panel = (rows below the diagonal block) inv(L_kk)^T, all of it or the rows of one chunk (chunk >= 0: absolute id)
+  const PanelGeom pg = panel_geom(p, k);
+  long long lo = pg.r0, hi = p->row_tiles;
+  if (chunk >= 0) {
+    if (chunk >= chunk_count_abs(pg.row_tiles, pg.cs)) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_factor_panel: no such chunk");
+    chunk_rows(pg, chunk, lo, hi);
+  }
+  if (hi > lo) {
+    GemmArgs g;
+    memset(&g, 0, sizeof g);
+    g.X = Acol; g.x_kstride = cstride;
+    g.Y = Wk; g.y_kstride = (long long)LG_BT * 64;
+    g.panel = panel; g.pg = pg;
+    g.mode = 0; g.rb0 = (int)(lo / LG_BLK); g.lcb0 = 0; g.world = p->world; g.rank = p->rank;
+    LCU(ctx, cudaFuncSetAttribute(large_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_SMEM));
+    cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+    large_gemm_kernel<<<dim3((unsigned)((hi - lo) / LG_BLK), LG_BT / LG_BLK), LG_THREADS, LG_SMEM, s>>>(g);
+    cngp_ctx_end(ctx);
+  }
   LCU(ctx, cudaGetLastError());
+  // 4. the panel is this block column of L: copy it back under the diagonal block (or leave that to cngp_large_copy_back)
+  if (!defer_copy_back) return cngp_large_copy_back(ctx, p, A, k, panel);
   return CNGP_OK;
 }
 
 extern "C" int cngp_large_update(cngp_ctx* ctx, const cngp_large_plan* p, double* A, int64_t k, const double* panel,
                                  int64_t c_lo, int64_t c_hi) {
-  return cngp_large_update_part(ctx, p, A, k, panel, c_lo, c_hi, CNGP_LARGE_ROWS_ALL);
+  return cngp_large_update_part(ctx, p, A, k, panel, c_lo, c_hi, CNGP_LARGE_ROWS_ALL, -1);
 }
 
 // rows: CNGP_LARGE_ROWS_ALL, or - for ONE block column - only its diagonal block (so that the block can be factored while
 // the rows below are still being updated on another stream) / only the rows below it.
 extern "C" int cngp_large_update_part(cngp_ctx* ctx, const cngp_large_plan* p, double* A, int64_t k, const double* panel,
-                                      int64_t c_lo, int64_t c_hi, int32_t rows) {
+                                      int64_t c_lo, int64_t c_hi, int32_t rows, int32_t chunk) {
   if (!ctx) return CNGP_ERR_INVALID;
   if (!p || !A || !panel || k < 0 || k >= p->n_blockcols) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_update: bad argument");
   c_lo = std::max<int64_t>(c_lo, k + 1);
@@ -594,21 +743,27 @@ extern "C" int cngp_large_update_part(cngp_ctx* ctx, const cngp_large_plan* p, d
   const int RB = (int)(p->row_tiles / LG_BLK);
   const long long c_first = l_lo * p->world + p->rank;
   const int rb0 = (int)(c_first * LG_BT / LG_BLK);
-  const long long r0 = (k + 1) * LG_BT;                     // compact panel layout, see cngp_large_factor_panel
-  const long long pstride = (p->row_tiles - r0) * 64;
+  const PanelGeom pg = panel_geom(p, k);
   GemmArgs g;
-  g.X = panel - r0 * 64; g.x_kstride = pstride;
-  g.Y = panel - r0 * 64; g.y_kstride = pstride;
+  memset(&g, 0, sizeof g);
+  g.panel = const_cast<double*>(panel); g.pg = pg;
   g.C = A; g.c_cstride = cstride;
   g.mode = 1; g.rb0 = rb0; g.world = p->world; g.rank = p->rank;
   LCU(ctx, cudaFuncSetAttribute(large_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_SMEM));
   const long long ncb = (l_hi - l_lo) * (LG_BT / LG_BLK);
   int rb_first = rb0, rb_count = RB - rb0;
-  if (rows != CNGP_LARGE_ROWS_ALL) {
+  if (rows != CNGP_LARGE_ROWS_ALL || chunk >= 0) {
     if (l_hi - l_lo != 1) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_update_part: a row part needs exactly one block column");
     const int diag_blocks = LG_BT / LG_BLK;
     if (rows == CNGP_LARGE_ROWS_DIAG) rb_count = diag_blocks;
-    else { rb_first = rb0 + diag_blocks; rb_count = RB - rb_first; }
+    else if (rows == CNGP_LARGE_ROWS_BELOW) { rb_first = rb0 + diag_blocks; rb_count = RB - rb_first; }
+    if (chunk >= 0) {        // ... intersected with the rows of one chunk of the panel
+      if (chunk >= chunk_count_abs(pg.row_tiles, pg.cs)) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_update_part: no such chunk");
+      long long lo, hi;
+      chunk_rows(pg, chunk, lo, hi);
+      const int b_lo = std::max<int>(rb_first, (int)(lo / LG_BLK)), b_hi = std::min<int>(rb_first + rb_count, (int)(hi / LG_BLK));
+      rb_first = b_lo; rb_count = b_hi - b_lo;
+    }
     if (rb_count <= 0) return CNGP_OK;
     g.rb0 = rb_first;
   }
@@ -656,7 +811,79 @@ extern "C" int cngp_large_backsolve_step(cngp_ctx* ctx, const cngp_large_plan* p
   large_back_partial_kernel<<<dim3(LG_BT, BACK_CHUNKS), 256, 0, s>>>(Acol, p->row_tiles, (j + 1) * LG_BT, NT, alpha, partial);
   cngp_ctx_end(ctx);
   cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
-  large_back_finish_kernel<<<1, 4 * LG_NB, 0, s>>>(winv + l * LG_BT * LG_BT * 64, z + j * LG_NB, partial, alpha + j * LG_NB);
+  large_back_finish_kernel<<<1, 4 * LG_NB, 0, s>>>(winv + l * LG_BT * LG_BT * 64, z + j * LG_NB, partial, BACK_CHUNKS, alpha + j * LG_NB);
+  cngp_ctx_end(ctx);
+  LCU(ctx, cudaGetLastError());
+  return CNGP_OK;
+}
+
+// The lazy backward sweep (see large_back_apply_kernel), last block column first:
+//   owner of j:  cngp_large_backsolve_finish  alpha_j = inv(L_jj)^T (z_j - s_j)      -> broadcast alpha_j
+//   every rank:  cngp_large_backsolve_apply   s_c += L(block row j, c)^T alpha_j for its block columns c < j
+// s [n_pad] starts as zeros.
+extern "C" int cngp_large_backsolve_finish(cngp_ctx* ctx, const cngp_large_plan* p, const double* winv, int64_t j,
+                                           const double* z, const double* s_acc, double* alpha) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!p || !winv || !z || !s_acc || !alpha || j < 0 || j >= p->n_blockcols)
+    return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_backsolve_finish: bad argument");
+  if (j % p->world != p->rank) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_backsolve_finish: not the owner");
+  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
+  const long long l = j / p->world;
+  cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+  large_back_finish_kernel<<<1, 4 * LG_NB, 0, cngp_ctx_stream(ctx)>>>(winv + l * LG_BT * LG_BT * 64, z + j * LG_NB,
+                                                                      s_acc + j * LG_NB, 1, alpha + j * LG_NB);
+  cngp_ctx_end(ctx);
+  LCU(ctx, cudaGetLastError());
+  return CNGP_OK;
+}
+
+extern "C" int cngp_large_backsolve_apply(cngp_ctx* ctx, const cngp_large_plan* p, const double* A, int64_t j,
+                                          int64_t c_hi, const double* alpha, double* s_acc) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!p || !A || !alpha || !s_acc || j < 0 || j >= p->n_blockcols)
+    return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_backsolve_apply: bad argument");
+  if (c_hi < 0 || c_hi > j) c_hi = j;
+  const long long n_lct = local_index_of(c_hi, p->world, p->rank) * LG_BT;  // local column tiles of block columns < c_hi
+  if (n_lct <= 0) return CNGP_OK;
+  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
+  cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+  large_back_apply_kernel<<<(unsigned)((n_lct + 7) / 8), 256, 0, cngp_ctx_stream(ctx)>>>(A, p->row_tiles, j, n_lct, p->world,
+                                                                                      p->rank, alpha + j * LG_NB, s_acc);
+  cngp_ctx_end(ctx);
+  LCU(ctx, cudaGetLastError());
+  return CNGP_OK;
+}
+
+// Grouped backward sweep (large.py): the serial part of a group of `world` consecutive block columns runs redundantly on
+// every rank from the replicated band, so the group costs one collective instead of one per block column.
+//   cngp_large_group_finish  alpha_j = inv(L_jj)^T (z_j - s_j), inv(L_jj) = band block (j, 0)        (any rank)
+//   cngp_large_group_apply   s_c += L(i, c)^T alpha_i for the block columns c in [c_lo, i), band blocks (c, i - c)
+// Same kernels' arithmetic as cngp_large_backsolve_finish / _apply: the results do not depend on the world size.
+extern "C" int cngp_large_group_finish(cngp_ctx* ctx, const cngp_large_plan* p, const double* band, int64_t n_local_max,
+                                       int64_t j, const double* z, const double* s_acc, double* alpha) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!p || !band || !z || !s_acc || !alpha || j < 0 || j >= p->n_blockcols || n_local_max <= 0)
+    return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_group_finish: bad argument");
+  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
+  const double* Wj = band + (((j % p->world) * n_local_max + j / p->world) * p->world) * BAND_BLK;
+  cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+  large_back_finish_kernel<<<1, 4 * LG_NB, 0, cngp_ctx_stream(ctx)>>>(Wj, z + j * LG_NB, s_acc + j * LG_NB, 1, alpha + j * LG_NB);
+  cngp_ctx_end(ctx);
+  LCU(ctx, cudaGetLastError());
+  return CNGP_OK;
+}
+
+extern "C" int cngp_large_group_apply(cngp_ctx* ctx, const cngp_large_plan* p, const double* band, int64_t n_local_max,
+                                      int64_t i, int64_t c_lo, const double* alpha, double* s_acc) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!p || !band || !alpha || !s_acc || i < 0 || i >= p->n_blockcols || c_lo < 0 || n_local_max <= 0 ||
+      i - c_lo >= p->world)
+    return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_group_apply: bad argument");
+  if (c_lo >= i) return CNGP_OK;
+  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
+  cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+  large_group_apply_kernel<<<dim3(LG_BT / 8, (unsigned)(i - c_lo)), 256, 0, cngp_ctx_stream(ctx)>>>(
+      band, n_local_max, p->world, p->world, i, c_lo, alpha + i * LG_NB, s_acc);
   cngp_ctx_end(ctx);
   LCU(ctx, cudaGetLastError());
   return CNGP_OK;
@@ -701,11 +928,11 @@ extern "C" int cngp_chol_large(cngp_ctx* ctx, const cngp_kernel* kernel, const d
   cngp_large_make_plan(N, 1, 0, &p);
   LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
   cudaStream_t s = cngp_ctx_stream(ctx);
-  DevMem dA, dP, dW, dld, dst, dz, dal, dsum, dx, dy;
+  DevMem dA, dP, dW, dld, dst, dz, dal, dsum, dx, dy, dsa;
   if (!dA.alloc(sizeof(double) * p.local_doubles) || !dP.alloc(sizeof(double) * p.panel_doubles) ||
       !dW.alloc(sizeof(double) * p.winv_doubles) || !dld.alloc(sizeof(double) * p.n_blockcols) ||
       !dst.alloc(sizeof(int) * p.n_blockcols) || !dz.alloc(sizeof(double) * p.n_pad) ||
-      !dal.alloc(sizeof(double) * p.n_pad) || !dsum.alloc(sizeof(double) * 4))
+      !dal.alloc(sizeof(double) * p.n_pad) || !dsum.alloc(sizeof(double) * 4) || !dsa.alloc(sizeof(double) * p.n_pad))
     return cngp_set_error(ctx, CNGP_ERR_NOMEM, "chol_large: device allocation failed");
   const double *d_x = x, *d_y = y;
   if (mem == CNGP_MEM_HOST) {
@@ -725,8 +952,11 @@ extern "C" int cngp_chol_large(cngp_ctx* ctx, const cngp_kernel* kernel, const d
   if ((rc = cngp_large_reduce(ctx, &p, (const double*)dA.p, (const double*)dld.p, (const int*)dst.p, (double*)dz.p, (double*)dsum.p))) return rc;
   if (alpha) {
     LCU(ctx, cudaMemsetAsync(dal.p, 0, sizeof(double) * p.n_pad, s));
-    for (int64_t j = p.n_blockcols - 1; j >= 0; --j)
-      if ((rc = cngp_large_backsolve_step(ctx, &p, (const double*)dA.p, (const double*)dW.p, j, (const double*)dz.p, (double*)dal.p))) return rc;
+    LCU(ctx, cudaMemsetAsync(dsa.p, 0, sizeof(double) * p.n_pad, s));
+    for (int64_t j = p.n_blockcols - 1; j >= 0; --j) {
+      if ((rc = cngp_large_backsolve_finish(ctx, &p, (const double*)dW.p, j, (const double*)dz.p, (const double*)dsa.p, (double*)dal.p))) return rc;
+      if ((rc = cngp_large_backsolve_apply(ctx, &p, (const double*)dA.p, j, -1, (const double*)dal.p, (double*)dsa.p))) return rc;
+    }
     LCU(ctx, cudaMemcpyAsync(alpha, dal.p, sizeof(double) * N, mem == CNGP_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
   }
   double sums[3];

@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -53,7 +54,8 @@ class LargeWindow:
     high-priority stream for the panel chain."""
     N_PANELS = 3
 
-    def __init__(self, ctx: GpContext, kernel, theta, x, y, rank: int = 0, world: int = 1):
+    def __init__(self, ctx: GpContext, kernel, theta, x, y, rank: int = 0, world: int = 1,
+                 chunk_rows: Optional[int] = None):
         self.ctx, self.lib = ctx, ctx.lib
         self.kernel = parse_kernel(kernel)
         self.theta = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))
@@ -66,6 +68,15 @@ class LargeWindow:
         self.rank, self.world = rank, world
         self.plan = make_plan(self.N, world, rank)
         p = self.plan
+        # panel chunks (cngp.h, chunk_blocks): the unit of the pipelined panel chain.  OFF by default: with NCCL broadcasts
+        # (~50 us each whatever the size) the pipelining loses more than it gains - 8 GPUs, N = 32768: 80-90 ms in one
+        # piece, 95 ms in chunks of 4096 rows, 107 ms in chunks of 2048 (profiles/bench_large_8gpu_c*_r02o.json)
+        if chunk_rows is None:
+            chunk_rows = int(os.environ.get("CNGP_LARGE_CHUNK_ROWS", "0"))
+        if chunk_rows > 0:
+            rb = int(p.row_tiles) // 16
+            cs = max(chunk_rows // 128, -(-rb // L.LARGE_MAX_CHUNKS))
+            p.chunk_blocks = cs + (cs & 1)
         self.n_blockcols, self.nb, self.n_pad = int(p.n_blockcols), L.LARGE_NB, int(p.n_pad)
         f64 = dict(dtype=torch.float64, device=dev)
         self.A = torch.empty(max(1, p.local_doubles), **f64)
@@ -77,7 +88,9 @@ class LargeWindow:
         self.status = torch.zeros(p.n_blockcols, dtype=torch.int32, device=dev)
         self.z = torch.zeros(p.n_pad, **f64)
         self.alpha = torch.zeros(p.n_pad, **f64)
+        self.s_acc = torch.zeros(p.n_pad, **f64)
         self.sums = torch.zeros(4, **f64)
+        self._chunk_cache: Dict[int, tuple] = {}
 
     def _bind(self):
         self.ctx._bind_stream(True)
@@ -94,6 +107,20 @@ class LargeWindow:
         rows = int(self.plan.row_tiles) - (k + 1) * (self.nb // 8)
         return self.panels[k % self.N_PANELS][: (self.nb // 8) * rows * 64]
 
+    def panel_chunks(self, k: int):
+        """-> (absolute id of the first chunk of panel k that holds rows, [contiguous views of the panel buffer, one per
+        chunk]): the broadcast payloads of panel k, in row order."""
+        if k not in self._chunk_cache:
+            first, count = C.c_int32(), C.c_int32()
+            offs = (C.c_int64 * (L.LARGE_MAX_CHUNKS + 1))()
+            rc = self.lib.cngp_large_panel_chunks(C.byref(self.plan), k, C.byref(first), C.byref(count), offs)
+            if rc != 0:
+                raise CngpError(f"cngp_large_panel_chunks(k={k}) failed (rc={rc})")
+            self._chunk_cache[k] = (int(first.value), [int(offs[i]) for i in range(count.value + 1)])
+        first, offs = self._chunk_cache[k]
+        buf = self.panels[k % self.N_PANELS]
+        return first, [buf[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+
     def assemble(self):
         self._bind()
         self._chk(self.lib.cngp_large_assemble(self.ctx.h, C.byref(self.plan), C.byref(self.kernel), self.theta.ctypes.data,
@@ -103,18 +130,19 @@ class LargeWindow:
     DEFER_COPY, DIAG_ONLY, PANEL_ONLY = 1, 2, 4          # cngp.h CNGP_LARGE_*
     ROWS_ALL, ROWS_DIAG, ROWS_BELOW = 0, 1, 2
 
-    def factor_panel(self, k: int, flags: int = 0):
+    def factor_panel(self, k: int, flags: int = 0, chunk: int = -1):
         self._bind()
         self._chk(self.lib.cngp_large_factor_panel_ex(self.ctx.h, C.byref(self.plan), self.A.data_ptr(), k,
                                                       self.panels[k % self.N_PANELS].data_ptr(), self.winv.data_ptr(),
-                                                      self.logdet.data_ptr(), self.status.data_ptr(), int(flags)),
+                                                      self.logdet.data_ptr(), self.status.data_ptr(), int(flags), int(chunk)),
                   "cngp_large_factor_panel")
 
-    def update_part(self, k: int, c: int, rows: int):
-        """Update block column c with panel k: its diagonal block only / only the rows below it."""
+    def update_part(self, k: int, c: int, rows: int, chunk: int = -1):
+        """Update block column c with panel k: its diagonal block only / only the rows below it / (chunk >= 0) only the
+        rows of one chunk of the panel."""
         self._bind()
         self._chk(self.lib.cngp_large_update_part(self.ctx.h, C.byref(self.plan), self.A.data_ptr(), k,
-                                                  self.panels[k % self.N_PANELS].data_ptr(), c, c + 1, rows),
+                                                  self.panels[k % self.N_PANELS].data_ptr(), c, c + 1, rows, int(chunk)),
                   "cngp_large_update_part")
 
     def copy_back(self, k: int):
@@ -141,6 +169,57 @@ class LargeWindow:
         self._chk(self.lib.cngp_large_backsolve_step(self.ctx.h, C.byref(self.plan), self.A.data_ptr(),
                                                      self.winv.data_ptr(), j, self.z.data_ptr(), self.alpha.data_ptr()),
                   "cngp_large_backsolve_step")
+
+    def backsolve_begin(self):
+        self.s_acc.zero_()
+
+    def backsolve_finish(self, j: int):
+        self._bind()
+        self._chk(self.lib.cngp_large_backsolve_finish(self.ctx.h, C.byref(self.plan), self.winv.data_ptr(), j,
+                                                       self.z.data_ptr(), self.s_acc.data_ptr(), self.alpha.data_ptr()),
+                  "cngp_large_backsolve_finish")
+
+    def backsolve_apply(self, j: int, c_hi: int = -1):
+        """s_c += L(block row j, c)^T alpha_j for this rank's block columns c < c_hi (default: all c < j)."""
+        self._bind()
+        self._chk(self.lib.cngp_large_backsolve_apply(self.ctx.h, C.byref(self.plan), self.A.data_ptr(), j, c_hi,
+                                                      self.alpha.data_ptr(), self.s_acc.data_ptr()),
+                  "cngp_large_backsolve_apply")
+
+    # grouped sweep (world > 1): the replicated band, see cngp.h cngp_large_group_finish
+    BLK = 32 * 32 * 64
+
+    def band_begin(self):
+        """Pack this rank's part of the band - per block column c: inv(L_cc) and the blocks L(c+d, c) inside c's group of
+        `world` block columns - and return the per-rank parts [world] to be broadcast, each from its rank."""
+        W, nblk = self.world, self.n_blockcols
+        self.n_local_max = -(-nblk // W)
+        if getattr(self, "band", None) is None:
+            self.band = torch.empty(W, self.n_local_max, W, self.BLK, dtype=torch.float64, device=self.A.device)
+        own = self.band[self.rank]
+        nt = self.nb // 8
+        A3 = self.A.view(-1, int(self.plan.row_tiles), 64)           # [local column tile][row tile][64]
+        for l in range(int(self.plan.n_local_blockcols)):
+            c = l * W + self.rank
+            own[l, 0].copy_(self.winv[l * self.BLK:(l + 1) * self.BLK])
+            for d in range(1, min((c // W + 1) * W, nblk) - c):
+                own[l, d].view(nt, nt, 64).copy_(A3[l * nt:(l + 1) * nt, (c + d) * nt:(c + d + 1) * nt])
+        return [self.band[r] for r in range(W)]
+
+    def s_blocks(self, c_lo: int, c_hi: int):
+        return self.s_acc[c_lo * self.nb:c_hi * self.nb]
+
+    def group_finish(self, j: int):
+        self._bind()
+        self._chk(self.lib.cngp_large_group_finish(self.ctx.h, C.byref(self.plan), self.band.data_ptr(), self.n_local_max, j,
+                                                   self.z.data_ptr(), self.s_acc.data_ptr(), self.alpha.data_ptr()),
+                  "cngp_large_group_finish")
+
+    def group_apply(self, i: int, c_lo: int):
+        self._bind()
+        self._chk(self.lib.cngp_large_group_apply(self.ctx.h, C.byref(self.plan), self.band.data_ptr(), self.n_local_max, i,
+                                                  c_lo, self.alpha.data_ptr(), self.s_acc.data_ptr()),
+                  "cngp_large_group_apply")
 
     def alpha_block(self, j: int):
         return self.alpha[j * self.nb:(j + 1) * self.nb]
@@ -240,8 +319,14 @@ def _factor_two_streams(engine, rank, world, coll, nblk, chain, pt):
     runs on a high-priority stream of its own, next to the trailing updates on the main stream:
       main,  step k: wait panel k; update column k+2 with it FIRST (event: that column is current through panel k),
                      then columns k+3...; event: panel k's buffer is no longer read
-      chain, step k: wait panel k, wait "column k+1 current through panel k-1", wait "the buffer of panel k-2 is free";
+      chain, step k: wait "column k+1 current through panel k-1", wait "the buffer of panel k-2 is free";
                      owner: update column k+1 with panel k, factor; everybody: broadcast panel k+1 into the third buffer.
+    and the chain itself is pipelined over CHUNKS of panel rows (engine.panel_chunks; fixed absolute row ranges, each a
+    contiguous payload): the owner of k+1 updates its diagonal block as soon as the FIRST chunk of panel k is there and
+    factors it while the later chunks are still arriving; on a side stream it updates the rows of chunk c of its column
+    when chunk c of panel k has arrived; the panel GEMM of chunk c follows and its broadcast starts while the GEMM of
+    chunk c+1 runs.  Per column the chain then costs about  first chunk + diagonal block + one chunk GEMM  instead of
+    whole broadcast + update + whole panel GEMM.
     Each block column still receives its updates in increasing panel order, so the results are the same bits."""
     main = torch.cuda.current_stream()
     side = engine.side_stream
@@ -249,35 +334,47 @@ def _factor_two_streams(engine, rank, world, coll, nblk, chain, pt):
     engine.assemble()
     if rank == 0 % world:
         engine.factor_panel(0)
-    pending = coll.broadcast_async(engine.panel_payload(0), src=0)
+    first, views = engine.panel_chunks(0)
+    pending = {first + i: coll.broadcast_async(v, src=0) for i, v in enumerate(views)}
     col_current = torch.cuda.Event()          # block column k+1 is current through panel k-1 (recorded on main)
     col_current.record(main)
     buffer_free = {}                          # k -> event: trailing update k done, panel k's buffer may be overwritten
     for k in range(nblk):
         pt.mark("wait_panel")
-        pending.wait()                                           # main: panel k is here
+        for w in pending.values():
+            w.wait()                                             # main: panel k is here, all of it
         nxt = k + 1
         if nxt < nblk:
             with torch.cuda.stream(chain):
-                pending.wait()                                   # chain: panel k is here
                 chain.wait_event(col_current)
                 if k - 2 in buffer_free:
                     chain.wait_event(buffer_free.pop(k - 2))     # panel k+1 goes where panel k-2 was
+                nxt_first, nxt_views = engine.panel_chunks(nxt)
+                nxt_pending = {}
                 if nxt % world == rank:
-                    # diagonal block first, then its factorisation + inversion (two single-CTA kernels, 165 us) WHILE the
-                    # rows below are brought up to date on the side stream; the panel GEMM needs both
+                    # diagonal block first (its panel rows are the head of the first chunk), then its factorisation +
+                    # inversion WHILE the rows below are brought up to date, chunk by chunk, on the side stream
+                    pending[min(pending)].wait()
                     engine.update_part(k, nxt, engine.ROWS_DIAG)
                     fork = torch.cuda.Event()
                     fork.record(chain)
+                    rows_current = {}
                     with torch.cuda.stream(side):
                         side.wait_event(fork)
-                        engine.update_part(k, nxt, engine.ROWS_BELOW)
-                        join = torch.cuda.Event()
-                        join.record(side)
+                        for c in sorted(pending):
+                            pending[c].wait()
+                            engine.update_part(k, nxt, engine.ROWS_BELOW, c)
+                            rows_current[c] = torch.cuda.Event()
+                            rows_current[c].record(side)
                     engine.factor_panel(nxt, engine.DIAG_ONLY)
-                    chain.wait_event(join)
-                    engine.factor_panel(nxt, engine.PANEL_ONLY | engine.DEFER_COPY)
-                nxt_pending = coll.broadcast_async(engine.panel_payload(nxt), src=nxt % world)
+                    for i, v in enumerate(nxt_views):
+                        c = nxt_first + i
+                        chain.wait_event(rows_current[c])
+                        engine.factor_panel(nxt, engine.PANEL_ONLY | engine.DEFER_COPY, c)
+                        nxt_pending[c] = coll.broadcast_async(v, src=nxt % world)
+                else:
+                    for i, v in enumerate(nxt_views):
+                        nxt_pending[nxt_first + i] = coll.broadcast_async(v, src=nxt % world)
             pt.mark("trailing_update")
             if k > 0 and k % world == rank:
                 engine.copy_back(k)                              # off the chain: main has waited for panel k above
@@ -292,6 +389,9 @@ def _factor_two_streams(engine, rank, world, coll, nblk, chain, pt):
     done = torch.cuda.Event()
     done.record(chain)
     main.wait_event(done)
+    done_side = torch.cuda.Event()
+    done_side.record(side)
+    main.wait_event(done_side)
     if nblk > 1 and (nblk - 1) % world == rank:
         engine.copy_back(nblk - 1)                               # the last panel has no rows below its diagonal block
 
@@ -335,10 +435,39 @@ def chol_large_distributed(engine, rank: int, world: int, coll=None, want_alpha:
     res.update(logdet=logdet, quad=quad, lml=0.5 * (-engine.N * LOG_2PI - logdet - quad))
     if want_alpha:
         pt.mark("backsolve")
-        for j in range(nblk - 1, -1, -1):
-            if j % world == rank:
-                engine.backsolve_step(j)
-            coll.broadcast_async(engine.alpha_block(j), src=j % world).wait()
+        if world > 1 and hasattr(engine, "group_finish") and not os.environ.get("CNGP_LARGE_NO_GROUPS"):
+            # grouped lazy sweep: a collective costs ~50 us whatever its size (NCCL broadcast of 2 KB on 8 GPUs), and the
+            # sweep has one dependent step per block column.  The part of L that couples the `world` consecutive block
+            # columns of a group - their inverted diagonal blocks and the blocks between them, <= 4 MB per column - is
+            # replicated up front (one broadcast per rank); then a group costs ONE all-reduce (the sums s_c its columns
+            # have collected from the block rows below the group) and every rank runs the group's serial part itself.
+            for r, part in enumerate(engine.band_begin()):
+                coll.broadcast_async(part, src=r).wait()
+            engine.backsolve_begin()
+            for g in range((nblk - 1) // world, -1, -1):
+                c_lo, c_hi = g * world, min((g + 1) * world, nblk)
+                coll.all_reduce_sum(engine.s_blocks(c_lo, c_hi))      # non-owners hold zeros: the sum is exact
+                for c in range(c_hi - 1, c_lo - 1, -1):
+                    engine.group_finish(c)
+                    engine.group_apply(c, c_lo)
+                if c_lo > 0:
+                    for c in range(c_hi - 1, c_lo - 1, -1):
+                        engine.backsolve_apply(c, c_lo)
+        elif hasattr(engine, "backsolve_apply"):
+            # lazy sweep: the owner only finishes its block (256 x 256), every rank then folds alpha_j into the sums of
+            # all its block columns to the left - the pass over the column is off the serial path
+            engine.backsolve_begin()
+            for j in range(nblk - 1, -1, -1):
+                if j % world == rank:
+                    engine.backsolve_finish(j)
+                coll.broadcast_async(engine.alpha_block(j), src=j % world).wait()
+                if j > 0:
+                    engine.backsolve_apply(j)
+        else:
+            for j in range(nblk - 1, -1, -1):
+                if j % world == rank:
+                    engine.backsolve_step(j)
+                coll.broadcast_async(engine.alpha_block(j), src=j % world).wait()
         res["alpha"] = engine.alpha[: engine.N]
     pt.mark("end")
     if pt.on:
@@ -348,9 +477,9 @@ def chol_large_distributed(engine, rank: int, world: int, coll=None, want_alpha:
 
 
 def chol_large(ctx: GpContext, kernel, theta, x, y, rank: int = 0, world: int = 1, coll=None, want_alpha: bool = True,
-               lookahead: bool = True) -> Dict[str, object]:
+               lookahead: bool = True, chunk_rows: Optional[int] = None) -> Dict[str, object]:
     """Convenience: build this rank's LargeWindow and run the distributed factorisation."""
-    win = LargeWindow(ctx, kernel, theta, x, y, rank=rank, world=world)
+    win = LargeWindow(ctx, kernel, theta, x, y, rank=rank, world=world, chunk_rows=chunk_rows)
     out = chol_large_distributed(win, rank, world, coll=coll, want_alpha=want_alpha, lookahead=lookahead)
     out["window"] = win
     return out

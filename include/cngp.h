@@ -290,7 +290,13 @@ typedef struct cngp_large_plan {
   int64_t local_doubles;     /* size of this rank's matrix storage A */
   int64_t panel_doubles;     /* size of one panel buffer */
   int64_t winv_doubles;      /* inverted diagonal blocks of the local block columns (kept for the back substitution) */
+  int64_t chunk_blocks;      /* 0 (cngp_large_make_plan): panels in one piece.  Otherwise the rows of every panel are cut at
+                              * multiples of chunk_blocks x 128 rows (even, >= row_tiles/16/CNGP_LARGE_MAX_CHUNKS) and each
+                              * piece is stored contiguously - the unit the multi-GPU driver pipelines (panel GEMM of a
+                              * chunk -> its broadcast -> the update of the next block column with it).  The caller sets it
+                              * after cngp_large_make_plan, the same on every rank. */
 } cngp_large_plan;
+#define CNGP_LARGE_MAX_CHUNKS 16
 int cngp_large_make_plan(int64_t N, int32_t world, int32_t rank, cngp_large_plan* plan);
 /* Fill this rank's block columns: Ky tiles on and below the diagonal blocks, the y row, identity padding. */
 int cngp_large_assemble(cngp_ctx* ctx, const cngp_large_plan* plan, const cngp_kernel* kernel, const double* theta,
@@ -312,12 +318,17 @@ int cngp_large_factor_panel(cngp_ctx* ctx, const cngp_large_plan* plan, double* 
 #define CNGP_LARGE_ROWS_ALL 0
 #define CNGP_LARGE_ROWS_DIAG 1
 #define CNGP_LARGE_ROWS_BELOW 2
+/* chunk >= 0 (absolute chunk id, see chunk_blocks): the panel rows of that chunk only; -1: all rows. */
 int cngp_large_factor_panel_ex(cngp_ctx* ctx, const cngp_large_plan* plan, double* A, int64_t k, double* panel,
-                            double* winv, double* logdet, int32_t* status, int32_t flags);
+                            double* winv, double* logdet, int32_t* status, int32_t flags, int32_t chunk);
 int cngp_large_copy_back(cngp_ctx* ctx, const cngp_large_plan* p, double* A, int64_t k, const double* panel);
-/* cngp_large_update restricted, for ONE block column, to its diagonal block or to the rows below it. */
+/* The chunks of panel k that hold rows: id of the first, how many, and offsets[0 .. count] (doubles) delimiting them in
+ * the panel buffer - chunk first + i is panel[offsets[i] .. offsets[i+1]), one contiguous broadcast payload. */
+int cngp_large_panel_chunks(const cngp_large_plan* plan, int64_t k, int32_t* first, int32_t* count, int64_t* offsets);
+/* cngp_large_update restricted, for ONE block column, to its diagonal block or to the rows below it, and / or
+ * (chunk >= 0) to the rows of one chunk of the panel. */
 int cngp_large_update_part(cngp_ctx* ctx, const cngp_large_plan* plan, double* A, int64_t k, const double* panel,
-                           int64_t c_lo, int64_t c_hi, int32_t rows);
+                           int64_t c_lo, int64_t c_hi, int32_t rows, int32_t chunk);
 /* Every rank: A(:, c) -= panel panel(c)^T for its block columns c in [max(c_lo, k+1), c_hi). */
 int cngp_large_update(cngp_ctx* ctx, const cngp_large_plan* plan, double* A, int64_t k, const double* panel,
                       int64_t c_lo, int64_t c_hi);
@@ -329,6 +340,22 @@ int cngp_large_reduce(cngp_ctx* ctx, const cngp_large_plan* plan, const double* 
  * from z and alpha of the later blocks (which must already be in `alpha` on this rank). */
 int cngp_large_backsolve_step(cngp_ctx* ctx, const cngp_large_plan* plan, const double* A, const double* winv,
                               int64_t j, const double* z, double* alpha);
+/* The same sweep with the work taken off its serial path: the owner of j finishes alpha_j = inv(L_jj)^T (z_j - s_j)
+ * (cngp_large_backsolve_finish), alpha_j is broadcast, and EVERY rank adds L(block row j, c)^T alpha_j to s_c for its block
+ * columns c < j (cngp_large_backsolve_apply).  s [n_pad] starts as zeros.  Same bits on every world size. */
+int cngp_large_backsolve_finish(cngp_ctx* ctx, const cngp_large_plan* plan, const double* winv, int64_t j, const double* z,
+                                const double* s, double* alpha);
+int cngp_large_backsolve_apply(cngp_ctx* ctx, const cngp_large_plan* plan, const double* A, int64_t j, int64_t c_hi,
+                               const double* alpha, double* s);   /* block columns c < c_hi only (c_hi < 0: all c < j) */
+/* Grouped sweep for world > 1: `band` is replicated on every rank - for block column c, block (c, 0) = inv(L_cc) (the
+ * layout of `winv`) and block (c, d) = L(c + d, c) (32 column tiles x 32 row tiles x 64) for the c + d inside c's group of
+ * `world` consecutive block columns, at band[(((c % world) n_local_max + c / world) world + d) 65536].  Within a group
+ * every rank runs the same finish / apply sequence on its copy (no collective); the sums s_c enter the group through one
+ * all-reduce and the columns to the left receive the group's alpha through cngp_large_backsolve_apply. */
+int cngp_large_group_finish(cngp_ctx* ctx, const cngp_large_plan* plan, const double* band, int64_t n_local_max, int64_t j,
+                            const double* z, const double* s, double* alpha);
+int cngp_large_group_apply(cngp_ctx* ctx, const cngp_large_plan* plan, const double* band, int64_t n_local_max, int64_t i,
+                           int64_t c_lo, const double* alpha, double* s);
 /* r = Ky v for the same covariance, evaluated on the fly (no matrix stored): the residual check of the solve. */
 int cngp_large_matvec(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, const double* x, const double* v,
                       int64_t N, double* r);

@@ -112,7 +112,7 @@ class ThreadCollectives:
         return C()
 
 
-def run_ranks(world, kname, th, x, y, lookahead=True):
+def run_ranks(world, kname, th, x, y, lookahead=True, chunk_rows=None):
     from corenav_gp_b200.api import GpContext
     coll = ThreadCollectives(world)
     outs, errs = [None] * world, []
@@ -123,7 +123,7 @@ def run_ranks(world, kname, th, x, y, lookahead=True):
             ctx = GpContext(device=0)
             with torch.cuda.stream(torch.cuda.Stream()):
                 o = large.chol_large(ctx, kname, th, x, y, rank=rank, world=world, coll=coll.for_rank(rank),
-                                     lookahead=lookahead)
+                                     lookahead=lookahead, chunk_rows=chunk_rows)
                 torch.cuda.synchronize()
             o["alpha"] = o["alpha"].cpu().numpy()
             o["block_logdet"] = o.pop("window").logdet.cpu().numpy()
@@ -149,8 +149,10 @@ def test_block_cyclic_ranks_equal_single_gpu(gp_ctx, world, N):
     th = np.array(theta)
     x, y = series(N)
     single = gp_ctx.chol_large(kname, th, x, y, want_alpha=True)
-    for look in (True, False):
-        outs = run_ranks(world, kname, th, x, y, lookahead=look)
+    # chunk_rows: the panel cut into pieces of that many rows (the pipelined chain of the two-stream schedule); 256 and
+    # 512 give up to 9 / 5 chunks at these sizes, None = the default (one chunk here)
+    for look, chunk_rows in ((True, None), (True, 256), (True, 512), (False, None), (False, 256)):
+        outs = run_ranks(world, kname, th, x, y, lookahead=look, chunk_rows=chunk_rows)
         for o in outs:
             assert o["pivot"] == 0
             assert rel(o["logdet"], single["logdet"]) < 1e-13 and rel(o["quad"], single["quad"]) < 1e-13

@@ -56,6 +56,7 @@ def run(ctx, N, reps, rank, world, lookahead=True):
     best = min(times)
     del win
     return {"N": N, "n_gpus": world, "lookahead": lookahead, "ms": times, "best_ms": best,
+            "median_ms": float(np.median(times)), "chunk_rows": int(os.environ.get("CNGP_LARGE_CHUNK_ROWS", "0")),
             "tflops_n3_over_3": N ** 3 / 3.0 / (best * 1e-3) * 1e-12, "lml": out["lml"],
             "logdet": out["logdet"], "quad": out["quad"], "residual": res,
             "rank0_kernel_ms_last_rep": prof_ms, "rank0_launches_last_rep": prof_n,
