@@ -96,6 +96,8 @@ SIGNATURES = {
     "cngp_large_backsolve_apply": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_i64, c_dp, c_dp]),
     "cngp_large_group_finish": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_i64, c_dp, c_dp, c_dp]),
     "cngp_large_group_apply": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_i64, c_i64, c_dp, c_dp]),
+    "cngp_large_group_sweep": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_dp, c_i64, c_i64, c_i64, c_dp, c_dp, c_dp]),
+    "cngp_large_band_pack": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_dp, c_dp]),
     "cngp_large_copy_back": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp]),
     "cngp_large_update_part": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_i64, c_i64, c_i32, c_i32]),
     "cngp_large_update": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_i64, c_i64]),

@@ -453,23 +453,34 @@ __device__ __forceinline__ void back_apply_column_tile(const double* col, const 
   }
 }
 
-__global__ void __launch_bounds__(256) large_back_apply_kernel(const double* A, long long row_tiles, long long j,
+// block rows j, j-1, ..., j-cnt+1 in that order (cnt <= BACK_APPLY_ROWS): the same additions as cnt launches of one row
+constexpr int BACK_APPLY_ROWS = 8;
+__global__ void __launch_bounds__(256) large_back_apply_kernel(const double* A, long long row_tiles, long long j, int cnt,
                                                                long long n_lct, int world, int rank,
-                                                               const double* alpha_j, double* s) {
-  __shared__ double al[LG_NB];
-  for (int i = threadIdx.x; i < LG_NB; i += blockDim.x) al[i] = alpha_j[i];
+                                                               const double* alpha, double* s) {
+  __shared__ double al[BACK_APPLY_ROWS][LG_NB];
+  for (int i = threadIdx.x; i < cnt * LG_NB; i += blockDim.x) al[i / LG_NB][i % LG_NB] = alpha[(j - i / LG_NB) * LG_NB + i % LG_NB];
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long lct = (long long)blockIdx.x * 8 + w;
   if (lct >= n_lct) return;
   const long long c = (lct / LG_BT) * world + rank;
-  back_apply_column_tile(A + (lct * row_tiles + j * LG_BT) * 64, al, s + 8 * (c * LG_BT + lct % LG_BT), lane);
+  for (int d = 0; d < cnt; ++d) {
+    back_apply_column_tile(A + (lct * row_tiles + (j - d) * LG_BT) * 64, al[d], s + 8 * (c * LG_BT + lct % LG_BT), lane);
+    __syncwarp();
+  }
 }
 
 // The same for the blocks of a GROUP of `world` consecutive block columns, read from the replicated band (every rank
 // holds, for every block column c, inv(L_cc) and the blocks L(c + d, c) that lie inside c's group):
-// s_c += L(i, c)^T alpha_i for c in [c_lo, i).  Block (c, d) of the band at band + (((c % world) nl + c / world) G + d) BLK.
+// s_c += L(i, c)^T alpha_i for c in [c_lo, i).
 constexpr long long BAND_BLK = (long long)LG_BT * LG_BT * 64;
+// block (c, d) of the band.  Rank r = c % world holds the columns at position r of their groups, which need world - r
+// blocks each (d = 0 .. world-1-r), so its part is [nl][world - r] blocks and starts after the parts of the ranks before it.
+__host__ __device__ inline const double* band_block(const double* band, long long nl, int world, long long c, long long d) {
+  const long long r = c % world;
+  return band + (nl * (r * world - r * (r - 1) / 2) + (c / world) * (world - r) + d) * BAND_BLK;
+}
 __global__ void __launch_bounds__(256) large_group_apply_kernel(const double* band, long long nl, int G, int world,
                                                                 long long i, long long c_lo, const double* alpha_i, double* s) {
   __shared__ double al[LG_NB];
@@ -478,7 +489,7 @@ __global__ void __launch_bounds__(256) large_group_apply_kernel(const double* ba
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long c = c_lo + blockIdx.y;
   const int ct = blockIdx.x * 8 + w;
-  const double* blk = band + (((c % world) * nl + c / world) * G + (i - c)) * BAND_BLK;
+  const double* blk = band_block(band, nl, world, c, i - c);
   back_apply_column_tile(blk + (long long)ct * LG_BT * 64, al, s + 8 * (c * LG_BT + ct), lane);
 }
 
@@ -847,8 +858,8 @@ extern "C" int cngp_large_backsolve_apply(cngp_ctx* ctx, const cngp_large_plan* 
   if (n_lct <= 0) return CNGP_OK;
   LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
   cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
-  large_back_apply_kernel<<<(unsigned)((n_lct + 7) / 8), 256, 0, cngp_ctx_stream(ctx)>>>(A, p->row_tiles, j, n_lct, p->world,
-                                                                                      p->rank, alpha + j * LG_NB, s_acc);
+  large_back_apply_kernel<<<(unsigned)((n_lct + 7) / 8), 256, 0, cngp_ctx_stream(ctx)>>>(A, p->row_tiles, j, 1, n_lct, p->world,
+                                                                                      p->rank, alpha, s_acc);
   cngp_ctx_end(ctx);
   LCU(ctx, cudaGetLastError());
   return CNGP_OK;
@@ -865,7 +876,7 @@ extern "C" int cngp_large_group_finish(cngp_ctx* ctx, const cngp_large_plan* p, 
   if (!p || !band || !z || !s_acc || !alpha || j < 0 || j >= p->n_blockcols || n_local_max <= 0)
     return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_group_finish: bad argument");
   LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
-  const double* Wj = band + (((j % p->world) * n_local_max + j / p->world) * p->world) * BAND_BLK;
+  const double* Wj = band_block(band, n_local_max, p->world, j, 0);
   cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
   large_back_finish_kernel<<<1, 4 * LG_NB, 0, cngp_ctx_stream(ctx)>>>(Wj, z + j * LG_NB, s_acc + j * LG_NB, 1, alpha + j * LG_NB);
   cngp_ctx_end(ctx);
@@ -886,6 +897,61 @@ extern "C" int cngp_large_group_apply(cngp_ctx* ctx, const cngp_large_plan* p, c
       band, n_local_max, p->world, p->world, i, c_lo, alpha + i * LG_NB, s_acc);
   cngp_ctx_end(ctx);
   LCU(ctx, cudaGetLastError());
+  return CNGP_OK;
+}
+
+// One group of the grouped sweep in one call (the per-column calls above, enqueued back to back - the sweep is a chain of
+// ~5 us kernels, and from Python the host could not enqueue them as fast as the GPU retires them): for c = c_hi-1 .. c_lo:
+// group_finish(c), group_apply(c, c_lo); then the group's alpha folded into this rank's block columns left of the group.
+extern "C" int cngp_large_group_sweep(cngp_ctx* ctx, const cngp_large_plan* p, const double* A, const double* band,
+                                      int64_t n_local_max, int64_t c_lo, int64_t c_hi, const double* z, double* s_acc,
+                                      double* alpha) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!p || !A || !band || !z || !s_acc || !alpha || c_lo < 0 || c_hi > p->n_blockcols || c_lo >= c_hi ||
+      c_hi - c_lo > p->world || n_local_max <= 0)
+    return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_group_sweep: bad argument");
+  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
+  cudaStream_t st = cngp_ctx_stream(ctx);
+  for (long long c = c_hi - 1; c >= c_lo; --c) {
+    const double* Wc = band_block(band, n_local_max, p->world, c, 0);
+    cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+    large_back_finish_kernel<<<1, 4 * LG_NB, 0, st>>>(Wc, z + c * LG_NB, s_acc + c * LG_NB, 1, alpha + c * LG_NB);
+    cngp_ctx_end(ctx);
+    if (c > c_lo) {
+      cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+      large_group_apply_kernel<<<dim3(LG_BT / 8, (unsigned)(c - c_lo)), 256, 0, st>>>(band, n_local_max, p->world, p->world, c, c_lo,
+                                                                                   alpha + c * LG_NB, s_acc);
+      cngp_ctx_end(ctx);
+    }
+  }
+  const long long n_lct = local_index_of(c_lo, p->world, p->rank) * LG_BT;
+  for (long long j = c_hi - 1; n_lct > 0 && j >= c_lo; j -= BACK_APPLY_ROWS) {
+    const int cnt = (int)std::min<long long>(BACK_APPLY_ROWS, j - c_lo + 1);
+    cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
+    large_back_apply_kernel<<<(unsigned)((n_lct + 7) / 8), 256, 0, st>>>(A, p->row_tiles, j, cnt, n_lct, p->world, p->rank, alpha, s_acc);
+    cngp_ctx_end(ctx);
+  }
+  LCU(ctx, cudaGetLastError());
+  return CNGP_OK;
+}
+
+// This rank's part of the band: per local block column l (global c = l world + rank) block 0 = inv(L_cc), block d =
+// L(c + d, c) for the c + d inside c's group.  band_own [n_local_blockcols][world - rank][65536].
+extern "C" int cngp_large_band_pack(cngp_ctx* ctx, const cngp_large_plan* p, const double* A, const double* winv, double* band_own) {
+  if (!ctx) return CNGP_ERR_INVALID;
+  if (!p || !A || !winv || !band_own) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_band_pack: bad argument");
+  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
+  cudaStream_t st = cngp_ctx_stream(ctx);
+  const long long cstride = p->row_tiles * 64;
+  for (long long l = 0; l < p->n_local_blockcols; ++l) {
+    const long long c = l * p->world + p->rank;
+    double* dst = band_own + l * (p->world - p->rank) * BAND_BLK;
+    LCU(ctx, cudaMemcpyAsync(dst, winv + l * BAND_BLK, sizeof(double) * BAND_BLK, cudaMemcpyDeviceToDevice, st));
+    const long long g_end = std::min<long long>((c / p->world + 1) * p->world, p->n_blockcols);
+    for (long long d = 1; c + d < g_end; ++d)
+      LCU(ctx, cudaMemcpy2DAsync(dst + d * BAND_BLK, (size_t)LG_BT * 512, A + l * LG_BT * cstride + (c + d) * LG_BT * 64, cstride * 8,
+                                 (size_t)LG_BT * 512, LG_BT, cudaMemcpyDeviceToDevice, st));
+  }
   return CNGP_OK;
 }
 

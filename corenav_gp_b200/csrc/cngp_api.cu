@@ -755,7 +755,8 @@ int cngp_lml_grad_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* t
       ga.x = d_x; ga.N = N; ga.nt = nt; ga.n_windows = (int)B; ga.problem0 = p0;
       ga.L = Lbuf; ga.W = Wbuf; ga.z = zbuf; ga.alpha = abuf; ga.status = d_status; ga.grad = d_grad;
       ga.skip = skip;
-      ga.lag_ok = fa.lag_ok;
+      // uniform-stamp contraction of gp_grad_kernel: stationary expressions, or few product terms with Brownian / Linear factors
+      ga.lag_ok = fa.lag_ok ? 1 : ((lag_tables_enabled() && kp.n_terms <= GRAD_UNI_TERMS) ? 2 : 0);
       ctx->begin(CNGP_PROF_GRAD);
       if (nt <= GRAD_SMEM_NT) {
         const size_t gsm = grad_smem_bytes(nt);

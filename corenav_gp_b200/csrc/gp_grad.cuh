@@ -38,8 +38,10 @@ struct GradArgs {
   const int* status;       // [n_problems]
   double* grad;            // [n_problems][P]
   const int* skip;         // [n_problems] or null: problems with skip[p] != 0 are left untouched
-  int lag_ok;              // the expression is stationary (host check): the uniform-stamp contraction may be used
+  int lag_ok;              // host check of the expression: 1 stationary, 2 at most GRAD_UNI_TERMS product terms with Brownian
+                           // / Linear factors - the uniform-stamp contraction may be used; 0 never
 };
+constexpr int GRAD_UNI_TERMS = 2;
 
 // tile^T in the lane layout: lane (r,q) gets T[2q][r], T[2q+1][r]
 __device__ __forceinline__ tile2 tile_load_T(const double* tile, int lane) {
@@ -64,9 +66,11 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32) gp_grad_kernel(const GradArgs
   __shared__ GradConst gcs[CNGP_MAX_LEAVES];
   // uniform mode: dL_dK summed along the diagonals of Ky - per tile diagonal D and in-tile diagonal delta = r - c (lag =
   // 8 D + delta); every (D, delta) cell has exactly one writer, so the sums do not depend on scheduling (no atomics)
-  __shared__ double sD[CNGP_MAX_N / 8 + 1][16];
+  __shared__ double sD[GRAD_UNI_TERMS][CNGP_MAX_N / 8 + 1][16];
   __shared__ __align__(16) double wst[GRAD_WARPS][64];
   __shared__ double sdiag;
+  __shared__ double sdg[CNGP_MAX_N + 8];               // lag_ok == 2: dL_dK on the true diagonal, entry by entry
+  __shared__ int t_nb[GRAD_UNI_TERMS], t_nl[GRAD_UNI_TERMS];   // Brownian / Linear factors of each product term
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int r = lane >> 2, q = lane & 3;
@@ -89,12 +93,20 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32) gp_grad_kernel(const GradArgs
   if (tid < a.kp.n_leaves) gcs[tid] = grad_prepare(a.kp.leaf_type[tid], th + a.kp.leaf_param[tid]);
   if (tid < a.kp.n_terms)
     for (int u = a.kp.term_start[tid]; u < a.kp.term_start[tid + 1]; ++u) { leaf_t0[u] = a.kp.term_start[tid]; leaf_t1[u] = a.kp.term_start[tid + 1]; }
+  if (a.lag_ok == 2 && tid < a.kp.n_terms) {
+    int nb = 0, nl = 0;
+    for (int u = a.kp.term_start[tid]; u < a.kp.term_start[tid + 1]; ++u) {
+      nb += a.kp.leaf_type[u] == CNGP_K_BROWNIAN;
+      nl += a.kp.leaf_type[u] == CNGP_K_LINEAR;
+    }
+    t_nb[tid] = nb; t_nl[tid] = nl;
+  }
   if (a.status[p] < 0) {  // factorisation failed: NaN gradient
     if (tid < P) a.grad[p * P + tid] = __longlong_as_double(0x7ff8000000000000LL);
     return;
   }
   // stamps x_i = x_0 + i exactly (integers below 2^26, so that the expanded-form r^2 is exact) and a stationary expression
-  int uni = a.lag_ok;
+  int uni = a.lag_ok != 0;
   for (int i = tid; i < N; i += GRAD_THREADS) {
     const double v = a.x[(long long)win * N + i], v0 = a.x[(long long)win * N];
     uni &= (v == v0 + (double)i) && (v0 == rint(v0)) && (fabs(v) < 67108864.0);
@@ -200,7 +212,7 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32) gp_grad_kernel(const GradArgs
   // added elementwise in registers (entries at the same place of those tiles share their lag 8 D + r - c), flushed once
   // per diagonal into N shared-memory bins - and dK/dtheta is evaluated once per LAG (N evaluations instead of N(N+1)/2
   // per leaf).  Tile diagonals are dealt to the warps in pairs (D, nt-1-D): nt + 1 tiles each, perfectly balanced.
-  if (uniform) {
+  if (uniform && a.lag_ok == 1) {
     double sd = 0.0;
     for (int pr = w; 2 * pr < nt; pr += GRAD_WARPS) {
       for (int half = 0; half < 2; ++half) {
@@ -236,7 +248,7 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32) gp_grad_kernel(const GradArgs
           const int dl = lane - 7;
           double ssum = 0.0;
           for (int rr = dl > 0 ? dl : 0; rr < (dl < 0 ? 8 + dl : 8); ++rr) ssum += wst[w][rr * 8 + rr - dl];
-          sD[D][lane] = ssum;
+          sD[0][D][lane] = ssum;
         }
         __syncwarp();
       }
@@ -251,12 +263,115 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32) gp_grad_kernel(const GradArgs
       if (!dg) {       // lag t = 8 D + delta: at most two tile diagonals carry it (three cells on tile diagonal 0)
         const int D = t >> 3, d8 = t & 7;
         wl = 0.0;
-        if (D == 0) wl = sD[0][7 + d8] + (d8 ? sD[0][7 - d8] : 0.0);
-        else if (D < nt) wl = sD[D][7 + d8];
-        if (d8 && D + 1 < nt) wl += sD[D + 1][d8 - 1];
+        if (D == 0) wl = sD[0][0][7 + d8] + (d8 ? sD[0][0][7 - d8] : 0.0);
+        else if (D < nt) wl = sD[0][D][7 + d8];
+        if (d8 && D + 1 < nt) wl += sD[0][D + 1][d8 - 1];
       }
       const double lagv = dg ? 0.0 : (double)t;
       if (wl != 0.0) contract(wl, lagv, 0.0, lagv * lagv, dg);
+    }
+  } else if (uniform) {
+    // lag_ok == 2 - product terms with Brownian / Linear factors (rbf*brownian, matern32+linear, ...) on the same uniform
+    // stamps.  Such a term is  (factors that depend on the lag only) x shape(a,b),  shape = the product of its Brownian
+    // min(|xa|,|xb|) and Linear xa xb factors without their variances.  So per term T the sums along the diagonals are
+    // taken of  dL_dK(a,b) shape_T(a,b)  (two fma per entry instead of a kernel-derivative evaluation), and the
+    // lag-only part - where a Brownian / Linear leaf counts as its variance, derivative 1 - is evaluated once per lag.
+    const int nterm = a.kp.n_terms;                    // <= GRAD_UNI_TERMS (host check)
+    const int nb0 = t_nb[0], nl0 = t_nl[0], nb1 = nterm > 1 ? t_nb[1] : 0, nl1 = nterm > 1 ? t_nl[1] : 0;
+    auto shape = [&](const double xa, const double xb, const int nb, const int nl) {
+      double m = 1.0;
+      if (nb) {
+        const bool agree = (xa > 0.0 && xb > 0.0) || (xa < 0.0 && xb < 0.0) || (xa == 0.0 && xb == 0.0);
+        const double bm = agree ? fmin(fabs(xa), fabs(xb)) : 0.0;
+        for (int i = 0; i < nb; ++i) m *= bm;
+      }
+      if (nl) {
+        const double lm = xa * xb;
+        for (int i = 0; i < nl; ++i) m *= lm;
+      }
+      return m;
+    };
+    for (int pr = w; 2 * pr < nt; pr += GRAD_WARPS) {
+      for (int half = 0; half < 2; ++half) {
+        const int D = half ? nt - 1 - pr : pr;
+        if (half && D == pr) break;
+        tile2 acc0{0.0, 0.0}, acc1{0.0, 0.0};
+        const double wsym = D == 0 ? 0.5 : 1.0;
+        for (int tb = 0; tb + D < nt; ++tb) {
+          const int ta = tb + D;
+          const double* pa = Wp + (long long)tile_index(ta, ta, nt) * 64;
+          const double* pb = Wp + (long long)tile_index(ta, tb, nt) * 64;
+          tile2 G0{0.0, 0.0}, G1{0.0, 0.0};
+          int m = ta;
+          for (; m + 1 < nt; m += 2) {
+            tile_mma(G0, tile_load(pa, lane), tile_load(pb, lane));
+            tile_mma(G1, tile_load(pa + 64, lane), tile_load(pb + 64, lane));
+            pa += 128; pb += 128;
+          }
+          if (m < nt) tile_mma(G0, tile_load(pa, lane), tile_load(pb, lane));
+          const int row = 8 * ta + r, c0 = 8 * tb + 2 * q;
+          double w0 = (row < N && c0 < N) ? wsym * (al[row] * al[c0] - (G0.a + G1.a)) : 0.0;
+          double w1 = (row < N && c0 + 1 < N) ? wsym * (al[row] * al[c0 + 1] - (G0.b + G1.b)) : 0.0;
+          if (D == 0) {      // the true diagonal is contracted entry by entry (same-point forms, White, noise)
+            if (row == c0) { sdg[row] = w0; w0 = 0.0; }
+            if (row == c0 + 1) { sdg[row] = w1; w1 = 0.0; }
+          }
+          const double xa = xs[row], xb0 = xs[c0], xb1 = xs[c0 + 1];
+          acc0.a = fma(w0, shape(xa, xb0, nb0, nl0), acc0.a);
+          acc0.b = fma(w1, shape(xa, xb1, nb0, nl0), acc0.b);
+          if (nterm > 1) {
+            acc1.a = fma(w0, shape(xa, xb0, nb1, nl1), acc1.a);
+            acc1.b = fma(w1, shape(xa, xb1, nb1, nl1), acc1.b);
+          }
+        }
+        for (int T = 0; T < nterm; ++T) {
+          tile_store(wst[w], lane, T == 0 ? acc0 : acc1);
+          __syncwarp();
+          if (lane < 15) {
+            const int dl = lane - 7;
+            double ssum = 0.0;
+            for (int rr = dl > 0 ? dl : 0; rr < (dl < 0 ? 8 + dl : 8); ++rr) ssum += wst[w][rr * 8 + rr - dl];
+            sD[T][D][lane] = ssum;
+          }
+          __syncwarp();
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += GRAD_THREADS) {      // the true diagonal
+      g[CNGP_MAX_PARAMS] += sdg[i];                    // noise: trace(dL_dK)
+      contract(sdg[i], xs[i], xs[i], 0.0, true);
+    }
+    for (int t = tid + 1; t < N; t += GRAD_THREADS) {  // off-diagonal lags
+      const int D = t >> 3, d8 = t & 7;
+      const double lagv = (double)t, r2 = lagv * lagv;
+      for (int T = 0; T < nterm; ++T) {
+        double wl = 0.0;
+        if (D == 0) wl = sD[T][0][7 + d8] + sD[T][0][7 - d8];
+        else if (D < nt) wl = sD[T][D][7 + d8];
+        if (d8 && D + 1 < nt) wl += sD[T][D + 1][d8 - 1];
+        if (wl == 0.0) continue;
+        const int u0 = a.kp.term_start[T], u1 = a.kp.term_start[T + 1];
+        for (int u = u0; u < u1; ++u) {
+          double others = 1.0, dv[3];
+          for (int u2 = u0; u2 < u1; ++u2) {
+            if (u2 == u) continue;
+            const int ty = a.kp.leaf_type[u2];
+            const bool ns = ty == CNGP_K_BROWNIAN || ty == CNGP_K_LINEAR;     // shape already in wl: value = variance
+            others *= leaf_value_grad_c<true>(ty, thv + a.kp.leaf_param[u2], gcs[u2], ns ? 1.0 : lagv, ns ? 1.0 : 0.0, r2, false, dv);
+          }
+          const int ty = a.kp.leaf_type[u];
+          const bool ns = ty == CNGP_K_BROWNIAN || ty == CNGP_K_LINEAR;
+          leaf_value_grad_c<true>(ty, thv + a.kp.leaf_param[u], gcs[u], ns ? 1.0 : lagv, ns ? 1.0 : 0.0, r2, false, dv);
+          const int np = leaf_nparams(ty), po = a.kp.leaf_param[u];
+          const double ww = wl * others;
+#pragma unroll
+          for (int i = 0; i < CNGP_MAX_PARAMS; ++i) {
+            const int jj = i - po;
+            if (jj >= 0 && jj < np) g[i] += ww * (jj == 0 ? dv[0] : (jj == 1 ? dv[1] : dv[2]));
+          }
+        }
+      }
     }
   } else {
   const int n_tiles = tiles_in_lower(nt);

@@ -193,18 +193,16 @@ class LargeWindow:
         """Pack this rank's part of the band - per block column c: inv(L_cc) and the blocks L(c+d, c) inside c's group of
         `world` block columns - and return the per-rank parts [world] to be broadcast, each from its rank."""
         W, nblk = self.world, self.n_blockcols
-        self.n_local_max = -(-nblk // W)
+        self.n_local_max = nl = -(-nblk // W)
         if getattr(self, "band", None) is None:
-            self.band = torch.empty(W, self.n_local_max, W, self.BLK, dtype=torch.float64, device=self.A.device)
-        own = self.band[self.rank]
-        nt = self.nb // 8
-        A3 = self.A.view(-1, int(self.plan.row_tiles), 64)           # [local column tile][row tile][64]
-        for l in range(int(self.plan.n_local_blockcols)):
-            c = l * W + self.rank
-            own[l, 0].copy_(self.winv[l * self.BLK:(l + 1) * self.BLK])
-            for d in range(1, min((c // W + 1) * W, nblk) - c):
-                own[l, d].view(nt, nt, 64).copy_(A3[l * nt:(l + 1) * nt, (c + d) * nt:(c + d + 1) * nt])
-        return [self.band[r] for r in range(W)]
+            self.band = torch.empty(nl * (W * (W + 1) // 2) * self.BLK, dtype=torch.float64, device=self.A.device)
+        # rank r's columns sit at position r of their groups and need W - r blocks each
+        offs = [nl * (r * W - r * (r - 1) // 2) * self.BLK for r in range(W + 1)]
+        parts = [self.band[offs[r]:offs[r + 1]] for r in range(W)]
+        self._bind()
+        self._chk(self.lib.cngp_large_band_pack(self.ctx.h, C.byref(self.plan), self.A.data_ptr(), self.winv.data_ptr(),
+                                                parts[self.rank].data_ptr()), "cngp_large_band_pack")
+        return parts
 
     def s_blocks(self, c_lo: int, c_hi: int):
         return self.s_acc[c_lo * self.nb:c_hi * self.nb]
@@ -214,6 +212,13 @@ class LargeWindow:
         self._chk(self.lib.cngp_large_group_finish(self.ctx.h, C.byref(self.plan), self.band.data_ptr(), self.n_local_max, j,
                                                    self.z.data_ptr(), self.s_acc.data_ptr(), self.alpha.data_ptr()),
                   "cngp_large_group_finish")
+
+    def group_sweep(self, c_lo: int, c_hi: int):
+        """group_finish / group_apply for c = c_hi-1 .. c_lo and the group's backsolve_apply, enqueued by one native call."""
+        self._bind()
+        self._chk(self.lib.cngp_large_group_sweep(self.ctx.h, C.byref(self.plan), self.A.data_ptr(), self.band.data_ptr(),
+                                                  self.n_local_max, c_lo, c_hi, self.z.data_ptr(), self.s_acc.data_ptr(),
+                                                  self.alpha.data_ptr()), "cngp_large_group_sweep")
 
     def group_apply(self, i: int, c_lo: int):
         self._bind()
@@ -447,6 +452,9 @@ def chol_large_distributed(engine, rank: int, world: int, coll=None, want_alpha:
             for g in range((nblk - 1) // world, -1, -1):
                 c_lo, c_hi = g * world, min((g + 1) * world, nblk)
                 coll.all_reduce_sum(engine.s_blocks(c_lo, c_hi))      # non-owners hold zeros: the sum is exact
+                if hasattr(engine, "group_sweep"):
+                    engine.group_sweep(c_lo, c_hi)                    # the same sequence, enqueued by one native call
+                    continue
                 for c in range(c_hi - 1, c_lo - 1, -1):
                     engine.group_finish(c)
                     engine.group_apply(c, c_lo)
