@@ -93,11 +93,7 @@ SIGNATURES = {
     "cngp_large_factor_panel_ex": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_dp, c_dp, c_ip, c_i32, c_i32]),
     "cngp_large_panel_chunks": (C.c_int, [C.POINTER(LargePlan), c_i64, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i64)]),
     "cngp_large_backsolve_finish": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_dp, c_dp]),
-    "cngp_large_backsolve_apply": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_i64, c_dp, c_dp]),
-    "cngp_large_group_finish": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_i64, c_dp, c_dp, c_dp]),
-    "cngp_large_group_apply": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_i64, c_i64, c_dp, c_dp]),
-    "cngp_large_group_sweep": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_dp, c_i64, c_i64, c_i64, c_dp, c_dp, c_dp]),
-    "cngp_large_band_pack": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_dp, c_dp]),
+    "cngp_large_backsolve_apply": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_dp]),
     "cngp_large_copy_back": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp]),
     "cngp_large_update_part": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_i64, c_i64, c_i32, c_i32]),
     "cngp_large_update": (C.c_int, [c_vp, C.POINTER(LargePlan), c_dp, c_i64, c_dp, c_i64, c_i64]),

@@ -403,10 +403,8 @@ __global__ void __launch_bounds__(256) large_back_partial_kernel(const double* A
 // alpha_j = inv(L_jj)^T (z_j - sum_chunks partial).  1024 threads: column c of the 256 x 256 inverse is summed in four
 // row segments of 64 (a single thread walking a whole column made this 39 us of pure load latency per block column -
 // 5 ms of the 128-step backward sweep).
-__global__ void __launch_bounds__(4 * LG_NB) large_back_finish_kernel(const double* W, const double* zj, const double* partial,
-                                                                      int nparts, double* alpha_j) {
-  __shared__ double t[LG_NB];
-  __shared__ double seg_sum[4][LG_NB];
+__device__ __forceinline__ void back_finish_block(const double* W, const double* zj, const double* partial, int nparts,
+                                                  double* alpha_j, double* t, double (*seg_sum)[LG_NB]) {
   const int c = threadIdx.x % LG_NB, seg = threadIdx.x / LG_NB;
   if (seg == 0) {
     double s = zj[c];
@@ -424,13 +422,13 @@ __global__ void __launch_bounds__(4 * LG_NB) large_back_finish_kernel(const doub
   if (seg == 0) alpha_j[c] = ((seg_sum[0][c] + seg_sum[1][c]) + seg_sum[2][c]) + seg_sum[3][c];
 }
 
-// The backward sweep the other way round ("lazy"): instead of the owner of block column j summing its whole column
-// against alpha when its turn comes (a pass over up to 67 MB on the serial path of every step), every rank adds the
-// contribution of alpha_j to ALL its block columns c < j as soon as alpha_j is known:
-//     s[8 ct + col] += sum_rows L(row in block row j, 8 ct + col) alpha_j[row]
-// so that when column j-1's turn comes its sum is complete after one 256-row slice.  One warp per column tile (32 tiles
-// of 512 B, contiguous); each column tile has one writer and receives its block rows in descending order on every world
-// size, so alpha has the same bits on 1 and on 8 GPUs.
+__global__ void __launch_bounds__(4 * LG_NB) large_back_finish_kernel(const double* W, const double* zj, const double* partial,
+                                                                      int nparts, double* alpha_j) {
+  __shared__ double t[LG_NB];
+  __shared__ double seg_sum[4][LG_NB];
+  back_finish_block(W, zj, partial, nparts, alpha_j, t, seg_sum);
+}
+
 // one warp: out[0..7] += sum over the 32 row tiles at `col` (consecutive tiles of one column tile) of tile^T alpha
 __device__ __forceinline__ void back_apply_column_tile(const double* col, const double* al, double* out, int lane) {
   const int r = lane >> 2, q = lane & 3;
@@ -453,44 +451,17 @@ __device__ __forceinline__ void back_apply_column_tile(const double* col, const 
   }
 }
 
-// block rows j, j-1, ..., j-cnt+1 in that order (cnt <= BACK_APPLY_ROWS): the same additions as cnt launches of one row
-constexpr int BACK_APPLY_ROWS = 8;
-__global__ void __launch_bounds__(256) large_back_apply_kernel(const double* A, long long row_tiles, long long j, int cnt,
+__global__ void __launch_bounds__(256) large_back_apply_kernel(const double* A, long long row_tiles, long long j,
                                                                long long n_lct, int world, int rank,
-                                                               const double* alpha, double* s) {
-  __shared__ double al[BACK_APPLY_ROWS][LG_NB];
-  for (int i = threadIdx.x; i < cnt * LG_NB; i += blockDim.x) al[i / LG_NB][i % LG_NB] = alpha[(j - i / LG_NB) * LG_NB + i % LG_NB];
+                                                               const double* alpha_j, double* s) {
+  __shared__ double al[LG_NB];
+  for (int i = threadIdx.x; i < LG_NB; i += blockDim.x) al[i] = alpha_j[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long lct = (long long)blockIdx.x * 8 + w;
   if (lct >= n_lct) return;
   const long long c = (lct / LG_BT) * world + rank;
-  for (int d = 0; d < cnt; ++d) {
-    back_apply_column_tile(A + (lct * row_tiles + (j - d) * LG_BT) * 64, al[d], s + 8 * (c * LG_BT + lct % LG_BT), lane);
-    __syncwarp();
-  }
-}
-
-// The same for the blocks of a GROUP of `world` consecutive block columns, read from the replicated band (every rank
-// holds, for every block column c, inv(L_cc) and the blocks L(c + d, c) that lie inside c's group):
-// s_c += L(i, c)^T alpha_i for c in [c_lo, i).
-constexpr long long BAND_BLK = (long long)LG_BT * LG_BT * 64;
-// block (c, d) of the band.  Rank r = c % world holds the columns at position r of their groups, which need world - r
-// blocks each (d = 0 .. world-1-r), so its part is [nl][world - r] blocks and starts after the parts of the ranks before it.
-__host__ __device__ inline const double* band_block(const double* band, long long nl, int world, long long c, long long d) {
-  const long long r = c % world;
-  return band + (nl * (r * world - r * (r - 1) / 2) + (c / world) * (world - r) + d) * BAND_BLK;
-}
-__global__ void __launch_bounds__(256) large_group_apply_kernel(const double* band, long long nl, int G, int world,
-                                                                long long i, long long c_lo, const double* alpha_i, double* s) {
-  __shared__ double al[LG_NB];
-  for (int t = threadIdx.x; t < LG_NB; t += blockDim.x) al[t] = alpha_i[t];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const long long c = c_lo + blockIdx.y;
-  const int ct = blockIdx.x * 8 + w;
-  const double* blk = band_block(band, nl, world, c, i - c);
-  back_apply_column_tile(blk + (long long)ct * LG_BT * 64, al, s + 8 * (c * LG_BT + ct), lane);
+  back_apply_column_tile(A + (lct * row_tiles + j * LG_BT) * 64, al, s + 8 * (c * LG_BT + lct % LG_BT), lane);
 }
 
 // r = Ky v with Ky evaluated on the fly; one warp per row
@@ -849,109 +820,18 @@ extern "C" int cngp_large_backsolve_finish(cngp_ctx* ctx, const cngp_large_plan*
 }
 
 extern "C" int cngp_large_backsolve_apply(cngp_ctx* ctx, const cngp_large_plan* p, const double* A, int64_t j,
-                                          int64_t c_hi, const double* alpha, double* s_acc) {
+                                          const double* alpha, double* s_acc) {
   if (!ctx) return CNGP_ERR_INVALID;
   if (!p || !A || !alpha || !s_acc || j < 0 || j >= p->n_blockcols)
     return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_backsolve_apply: bad argument");
-  if (c_hi < 0 || c_hi > j) c_hi = j;
-  const long long n_lct = local_index_of(c_hi, p->world, p->rank) * LG_BT;  // local column tiles of block columns < c_hi
+  const long long n_lct = local_index_of(j, p->world, p->rank) * LG_BT;     // local column tiles of block columns < j
   if (n_lct <= 0) return CNGP_OK;
   LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
   cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
-  large_back_apply_kernel<<<(unsigned)((n_lct + 7) / 8), 256, 0, cngp_ctx_stream(ctx)>>>(A, p->row_tiles, j, 1, n_lct, p->world,
-                                                                                      p->rank, alpha, s_acc);
+  large_back_apply_kernel<<<(unsigned)((n_lct + 7) / 8), 256, 0, cngp_ctx_stream(ctx)>>>(A, p->row_tiles, j, n_lct, p->world,
+                                                                                      p->rank, alpha + j * LG_NB, s_acc);
   cngp_ctx_end(ctx);
   LCU(ctx, cudaGetLastError());
-  return CNGP_OK;
-}
-
-// Grouped backward sweep (large.py): the serial part of a group of `world` consecutive block columns runs redundantly on
-// every rank from the replicated band, so the group costs one collective instead of one per block column.
-//   cngp_large_group_finish  alpha_j = inv(L_jj)^T (z_j - s_j), inv(L_jj) = band block (j, 0)        (any rank)
-//   cngp_large_group_apply   s_c += L(i, c)^T alpha_i for the block columns c in [c_lo, i), band blocks (c, i - c)
-// Same kernels' arithmetic as cngp_large_backsolve_finish / _apply: the results do not depend on the world size.
-extern "C" int cngp_large_group_finish(cngp_ctx* ctx, const cngp_large_plan* p, const double* band, int64_t n_local_max,
-                                       int64_t j, const double* z, const double* s_acc, double* alpha) {
-  if (!ctx) return CNGP_ERR_INVALID;
-  if (!p || !band || !z || !s_acc || !alpha || j < 0 || j >= p->n_blockcols || n_local_max <= 0)
-    return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_group_finish: bad argument");
-  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
-  const double* Wj = band_block(band, n_local_max, p->world, j, 0);
-  cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
-  large_back_finish_kernel<<<1, 4 * LG_NB, 0, cngp_ctx_stream(ctx)>>>(Wj, z + j * LG_NB, s_acc + j * LG_NB, 1, alpha + j * LG_NB);
-  cngp_ctx_end(ctx);
-  LCU(ctx, cudaGetLastError());
-  return CNGP_OK;
-}
-
-extern "C" int cngp_large_group_apply(cngp_ctx* ctx, const cngp_large_plan* p, const double* band, int64_t n_local_max,
-                                      int64_t i, int64_t c_lo, const double* alpha, double* s_acc) {
-  if (!ctx) return CNGP_ERR_INVALID;
-  if (!p || !band || !alpha || !s_acc || i < 0 || i >= p->n_blockcols || c_lo < 0 || n_local_max <= 0 ||
-      i - c_lo >= p->world)
-    return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_group_apply: bad argument");
-  if (c_lo >= i) return CNGP_OK;
-  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
-  cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
-  large_group_apply_kernel<<<dim3(LG_BT / 8, (unsigned)(i - c_lo)), 256, 0, cngp_ctx_stream(ctx)>>>(
-      band, n_local_max, p->world, p->world, i, c_lo, alpha + i * LG_NB, s_acc);
-  cngp_ctx_end(ctx);
-  LCU(ctx, cudaGetLastError());
-  return CNGP_OK;
-}
-
-// One group of the grouped sweep in one call (the per-column calls above, enqueued back to back - the sweep is a chain of
-// ~5 us kernels, and from Python the host could not enqueue them as fast as the GPU retires them): for c = c_hi-1 .. c_lo:
-// group_finish(c), group_apply(c, c_lo); then the group's alpha folded into this rank's block columns left of the group.
-extern "C" int cngp_large_group_sweep(cngp_ctx* ctx, const cngp_large_plan* p, const double* A, const double* band,
-                                      int64_t n_local_max, int64_t c_lo, int64_t c_hi, const double* z, double* s_acc,
-                                      double* alpha) {
-  if (!ctx) return CNGP_ERR_INVALID;
-  if (!p || !A || !band || !z || !s_acc || !alpha || c_lo < 0 || c_hi > p->n_blockcols || c_lo >= c_hi ||
-      c_hi - c_lo > p->world || n_local_max <= 0)
-    return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_group_sweep: bad argument");
-  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
-  cudaStream_t st = cngp_ctx_stream(ctx);
-  for (long long c = c_hi - 1; c >= c_lo; --c) {
-    const double* Wc = band_block(band, n_local_max, p->world, c, 0);
-    cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
-    large_back_finish_kernel<<<1, 4 * LG_NB, 0, st>>>(Wc, z + c * LG_NB, s_acc + c * LG_NB, 1, alpha + c * LG_NB);
-    cngp_ctx_end(ctx);
-    if (c > c_lo) {
-      cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
-      large_group_apply_kernel<<<dim3(LG_BT / 8, (unsigned)(c - c_lo)), 256, 0, st>>>(band, n_local_max, p->world, p->world, c, c_lo,
-                                                                                   alpha + c * LG_NB, s_acc);
-      cngp_ctx_end(ctx);
-    }
-  }
-  const long long n_lct = local_index_of(c_lo, p->world, p->rank) * LG_BT;
-  for (long long j = c_hi - 1; n_lct > 0 && j >= c_lo; j -= BACK_APPLY_ROWS) {
-    const int cnt = (int)std::min<long long>(BACK_APPLY_ROWS, j - c_lo + 1);
-    cngp_ctx_begin(ctx, CNGP_PROF_LARGE);
-    large_back_apply_kernel<<<(unsigned)((n_lct + 7) / 8), 256, 0, st>>>(A, p->row_tiles, j, cnt, n_lct, p->world, p->rank, alpha, s_acc);
-    cngp_ctx_end(ctx);
-  }
-  LCU(ctx, cudaGetLastError());
-  return CNGP_OK;
-}
-
-// This rank's part of the band: per local block column l (global c = l world + rank) block 0 = inv(L_cc), block d =
-// L(c + d, c) for the c + d inside c's group.  band_own [n_local_blockcols][world - rank][65536].
-extern "C" int cngp_large_band_pack(cngp_ctx* ctx, const cngp_large_plan* p, const double* A, const double* winv, double* band_own) {
-  if (!ctx) return CNGP_ERR_INVALID;
-  if (!p || !A || !winv || !band_own) return cngp_set_error(ctx, CNGP_ERR_INVALID, "large_band_pack: bad argument");
-  LCU(ctx, cudaSetDevice(cngp_ctx_device(ctx)));
-  cudaStream_t st = cngp_ctx_stream(ctx);
-  const long long cstride = p->row_tiles * 64;
-  for (long long l = 0; l < p->n_local_blockcols; ++l) {
-    const long long c = l * p->world + p->rank;
-    double* dst = band_own + l * (p->world - p->rank) * BAND_BLK;
-    LCU(ctx, cudaMemcpyAsync(dst, winv + l * BAND_BLK, sizeof(double) * BAND_BLK, cudaMemcpyDeviceToDevice, st));
-    const long long g_end = std::min<long long>((c / p->world + 1) * p->world, p->n_blockcols);
-    for (long long d = 1; c + d < g_end; ++d)
-      LCU(ctx, cudaMemcpy2DAsync(dst + d * BAND_BLK, (size_t)LG_BT * 512, A + l * LG_BT * cstride + (c + d) * LG_BT * 64, cstride * 8,
-                                 (size_t)LG_BT * 512, LG_BT, cudaMemcpyDeviceToDevice, st));
-  }
   return CNGP_OK;
 }
 
@@ -1021,7 +901,7 @@ extern "C" int cngp_chol_large(cngp_ctx* ctx, const cngp_kernel* kernel, const d
     LCU(ctx, cudaMemsetAsync(dsa.p, 0, sizeof(double) * p.n_pad, s));
     for (int64_t j = p.n_blockcols - 1; j >= 0; --j) {
       if ((rc = cngp_large_backsolve_finish(ctx, &p, (const double*)dW.p, j, (const double*)dz.p, (const double*)dsa.p, (double*)dal.p))) return rc;
-      if ((rc = cngp_large_backsolve_apply(ctx, &p, (const double*)dA.p, j, -1, (const double*)dal.p, (double*)dsa.p))) return rc;
+      if ((rc = cngp_large_backsolve_apply(ctx, &p, (const double*)dA.p, j, (const double*)dal.p, (double*)dsa.p))) return rc;
     }
     LCU(ctx, cudaMemcpyAsync(alpha, dal.p, sizeof(double) * N, mem == CNGP_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
   }

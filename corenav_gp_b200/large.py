@@ -179,52 +179,12 @@ class LargeWindow:
                                                        self.z.data_ptr(), self.s_acc.data_ptr(), self.alpha.data_ptr()),
                   "cngp_large_backsolve_finish")
 
-    def backsolve_apply(self, j: int, c_hi: int = -1):
-        """s_c += L(block row j, c)^T alpha_j for this rank's block columns c < c_hi (default: all c < j)."""
+    def backsolve_apply(self, j: int):
+        """s_c += L(block row j, c)^T alpha_j for this rank's block columns c < j."""
         self._bind()
-        self._chk(self.lib.cngp_large_backsolve_apply(self.ctx.h, C.byref(self.plan), self.A.data_ptr(), j, c_hi,
+        self._chk(self.lib.cngp_large_backsolve_apply(self.ctx.h, C.byref(self.plan), self.A.data_ptr(), j,
                                                       self.alpha.data_ptr(), self.s_acc.data_ptr()),
                   "cngp_large_backsolve_apply")
-
-    # grouped sweep (world > 1): the replicated band, see cngp.h cngp_large_group_finish
-    BLK = 32 * 32 * 64
-
-    def band_begin(self):
-        """Pack this rank's part of the band - per block column c: inv(L_cc) and the blocks L(c+d, c) inside c's group of
-        `world` block columns - and return the per-rank parts [world] to be broadcast, each from its rank."""
-        W, nblk = self.world, self.n_blockcols
-        self.n_local_max = nl = -(-nblk // W)
-        if getattr(self, "band", None) is None:
-            self.band = torch.empty(nl * (W * (W + 1) // 2) * self.BLK, dtype=torch.float64, device=self.A.device)
-        # rank r's columns sit at position r of their groups and need W - r blocks each
-        offs = [nl * (r * W - r * (r - 1) // 2) * self.BLK for r in range(W + 1)]
-        parts = [self.band[offs[r]:offs[r + 1]] for r in range(W)]
-        self._bind()
-        self._chk(self.lib.cngp_large_band_pack(self.ctx.h, C.byref(self.plan), self.A.data_ptr(), self.winv.data_ptr(),
-                                                parts[self.rank].data_ptr()), "cngp_large_band_pack")
-        return parts
-
-    def s_blocks(self, c_lo: int, c_hi: int):
-        return self.s_acc[c_lo * self.nb:c_hi * self.nb]
-
-    def group_finish(self, j: int):
-        self._bind()
-        self._chk(self.lib.cngp_large_group_finish(self.ctx.h, C.byref(self.plan), self.band.data_ptr(), self.n_local_max, j,
-                                                   self.z.data_ptr(), self.s_acc.data_ptr(), self.alpha.data_ptr()),
-                  "cngp_large_group_finish")
-
-    def group_sweep(self, c_lo: int, c_hi: int):
-        """group_finish / group_apply for c = c_hi-1 .. c_lo and the group's backsolve_apply, enqueued by one native call."""
-        self._bind()
-        self._chk(self.lib.cngp_large_group_sweep(self.ctx.h, C.byref(self.plan), self.A.data_ptr(), self.band.data_ptr(),
-                                                  self.n_local_max, c_lo, c_hi, self.z.data_ptr(), self.s_acc.data_ptr(),
-                                                  self.alpha.data_ptr()), "cngp_large_group_sweep")
-
-    def group_apply(self, i: int, c_lo: int):
-        self._bind()
-        self._chk(self.lib.cngp_large_group_apply(self.ctx.h, C.byref(self.plan), self.band.data_ptr(), self.n_local_max, i,
-                                                  c_lo, self.alpha.data_ptr(), self.s_acc.data_ptr()),
-                  "cngp_large_group_apply")
 
     def alpha_block(self, j: int):
         return self.alpha[j * self.nb:(j + 1) * self.nb]
@@ -440,30 +400,13 @@ def chol_large_distributed(engine, rank: int, world: int, coll=None, want_alpha:
     res.update(logdet=logdet, quad=quad, lml=0.5 * (-engine.N * LOG_2PI - logdet - quad))
     if want_alpha:
         pt.mark("backsolve")
-        if world > 1 and hasattr(engine, "group_finish") and not os.environ.get("CNGP_LARGE_NO_GROUPS"):
-            # grouped lazy sweep: a collective costs ~50 us whatever its size (NCCL broadcast of 2 KB on 8 GPUs), and the
-            # sweep has one dependent step per block column.  The part of L that couples the `world` consecutive block
-            # columns of a group - their inverted diagonal blocks and the blocks between them, <= 4 MB per column - is
-            # replicated up front (one broadcast per rank); then a group costs ONE all-reduce (the sums s_c its columns
-            # have collected from the block rows below the group) and every rank runs the group's serial part itself.
-            for r, part in enumerate(engine.band_begin()):
-                coll.broadcast_async(part, src=r).wait()
-            engine.backsolve_begin()
-            for g in range((nblk - 1) // world, -1, -1):
-                c_lo, c_hi = g * world, min((g + 1) * world, nblk)
-                coll.all_reduce_sum(engine.s_blocks(c_lo, c_hi))      # non-owners hold zeros: the sum is exact
-                if hasattr(engine, "group_sweep"):
-                    engine.group_sweep(c_lo, c_hi)                    # the same sequence, enqueued by one native call
-                    continue
-                for c in range(c_hi - 1, c_lo - 1, -1):
-                    engine.group_finish(c)
-                    engine.group_apply(c, c_lo)
-                if c_lo > 0:
-                    for c in range(c_hi - 1, c_lo - 1, -1):
-                        engine.backsolve_apply(c, c_lo)
-        elif hasattr(engine, "backsolve_apply"):
+        if hasattr(engine, "backsolve_apply"):
             # lazy sweep: the owner only finishes its block (256 x 256), every rank then folds alpha_j into the sums of
-            # all its block columns to the left - the pass over the column is off the serial path
+            # all its block columns to the left - the pass over the column is off the serial path.  What is left per
+            # block column is the broadcast itself (~50 us for 2 KB on 8 GPUs).  Measured and not kept: replicating the
+            # blocks that couple `world` consecutive block columns so that a group costs one all-reduce and every rank
+            # runs its serial part alone - 8 GPUs: 90.7 ms against 89.2 ms (the group's 18 MB of blocks read by
+            # one CTA, or its 16 dependent small kernels, cost what the seven broadcasts did)
             engine.backsolve_begin()
             for j in range(nblk - 1, -1, -1):
                 if j % world == rank:

@@ -345,24 +345,8 @@ int cngp_large_backsolve_step(cngp_ctx* ctx, const cngp_large_plan* plan, const 
  * columns c < j (cngp_large_backsolve_apply).  s [n_pad] starts as zeros.  Same bits on every world size. */
 int cngp_large_backsolve_finish(cngp_ctx* ctx, const cngp_large_plan* plan, const double* winv, int64_t j, const double* z,
                                 const double* s, double* alpha);
-int cngp_large_backsolve_apply(cngp_ctx* ctx, const cngp_large_plan* plan, const double* A, int64_t j, int64_t c_hi,
-                               const double* alpha, double* s);   /* block columns c < c_hi only (c_hi < 0: all c < j) */
-/* Grouped sweep for world > 1: `band` is replicated on every rank - for block column c, block (c, 0) = inv(L_cc) (the
- * layout of `winv`) and block (c, d) = L(c + d, c) (32 column tiles x 32 row tiles x 64) for the c + d inside c's group of
- * `world` consecutive block columns.  Rank r = c % world holds the columns at position r of their groups, world - r blocks
- * each: its part is [n_local_max][world - r][65536] and the parts follow each other in rank order.  Within a group
- * every rank runs the same finish / apply sequence on its copy (no collective); the sums s_c enter the group through one
- * all-reduce and the columns to the left receive the group's alpha through cngp_large_backsolve_apply. */
-int cngp_large_group_finish(cngp_ctx* ctx, const cngp_large_plan* plan, const double* band, int64_t n_local_max, int64_t j,
-                            const double* z, const double* s, double* alpha);
-int cngp_large_group_apply(cngp_ctx* ctx, const cngp_large_plan* plan, const double* band, int64_t n_local_max, int64_t i,
-                           int64_t c_lo, const double* alpha, double* s);
-/* One whole group [c_lo, c_hi) in one call: finish / apply for c = c_hi-1 .. c_lo, then cngp_large_backsolve_apply of the
- * group's block rows to this rank's block columns < c_lo (same arithmetic, enqueued back to back). */
-int cngp_large_group_sweep(cngp_ctx* ctx, const cngp_large_plan* plan, const double* A, const double* band, int64_t n_local_max,
-                           int64_t c_lo, int64_t c_hi, const double* z, double* s, double* alpha);
-/* This rank's part of the band, [n_local_blockcols][world - rank][65536] (to be exchanged by the caller). */
-int cngp_large_band_pack(cngp_ctx* ctx, const cngp_large_plan* plan, const double* A, const double* winv, double* band_own);
+int cngp_large_backsolve_apply(cngp_ctx* ctx, const cngp_large_plan* plan, const double* A, int64_t j, const double* alpha,
+                               double* s);
 /* r = Ky v for the same covariance, evaluated on the fly (no matrix stored): the residual check of the solve. */
 int cngp_large_matvec(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, const double* x, const double* v,
                       int64_t N, double* r);

@@ -82,37 +82,10 @@ class DenseEngine:
         t = self.z[j * NB:(j + 1) * NB] - self.s_acc[j * NB:(j + 1) * NB]
         self.alpha[j * NB:(j + 1) * NB] = self.diag_inv[j].T @ t
 
-    def backsolve_apply(self, j, c_hi=-1):
-        c_hi = j if c_hi < 0 else c_hi
+    def backsolve_apply(self, j):
         for c, blk in self.cols.items():
-            if c < c_hi:
+            if c < j:
                 self.s_acc[c * NB:(c + 1) * NB] += blk[j * NB:(j + 1) * NB].T @ self.alpha[j * NB:(j + 1) * NB]
-
-    # the grouped sweep: replicated band[rank][local column][d] = inv(L_cc) (d = 0) / L(c+d, c) inside c's group
-    def band_begin(self):
-        W = self.world
-        nl = -(-self.n_blockcols // W)
-        self.band = torch.zeros(W, nl, W, NB, NB, dtype=torch.float64)
-        for c, blk in self.cols.items():
-            l = c // W
-            self.band[self.rank, l, 0] = self.diag_inv[c]
-            for d in range(1, min((c // W + 1) * W, self.n_blockcols) - c):
-                self.band[self.rank, l, d] = blk[(c + d) * NB:(c + d + 1) * NB]
-        return [self.band[r] for r in range(W)]
-
-    def s_blocks(self, c_lo, c_hi):
-        return self.s_acc[c_lo * NB:c_hi * NB]
-
-    def group_finish(self, j):
-        self.calls.append(("group_finish", j))
-        W = self.world
-        t = self.z[j * NB:(j + 1) * NB] - self.s_acc[j * NB:(j + 1) * NB]
-        self.alpha[j * NB:(j + 1) * NB] = self.band[j % W, j // W, 0].T @ t
-
-    def group_apply(self, i, c_lo):
-        W = self.world
-        for c in range(c_lo, i):
-            self.s_acc[c * NB:(c + 1) * NB] += self.band[c % W, c // W, i - c].T @ self.alpha[i * NB:(i + 1) * NB]
 
     def alpha_block(self, j):
         return self.alpha[j * NB:(j + 1) * NB]
