@@ -51,27 +51,46 @@ __global__ void opt_init_kernel(Optimizer* st, const double* theta0, long long t
 }
 
 // Consume the objective / gradient evaluated at every still-active window's trial point and publish the next one.
-__global__ void opt_feed_kernel(Optimizer* st, const double* lml, const double* grad, const int* status, int P,
-                                long long B, double* theta, int* done, int* n_active) {
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per window: the 5 KB state machine is copied into shared memory by the 32 lanes (coalesced), lane 0 runs the
+// L-BFGS-B step on the shared copy, and the lanes copy it back.  (One THREAD per window walking its state in global memory
+// - a few thousand dependent, uncoalesced accesses - took longer per iteration at B = 4096 than the factorisations:
+// tools/bench_configs.py callback, 105 ms per call of which 51 ms in gp_fit_kernel + gp_grad_kernel.)
+constexpr int FEED_WPB = 8;
+static_assert(sizeof(Optimizer) % 8 == 0, "Optimizer is copied as 64-bit words");
+__global__ void __launch_bounds__(FEED_WPB * 32) opt_feed_kernel(Optimizer* st, const double* lml, const double* grad,
+                                                                 const int* status, int P, long long B, double* theta,
+                                                                 int* done, int* n_active) {
+  extern __shared__ __align__(16) unsigned char feed_sm[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = (long long)blockIdx.x * FEED_WPB + w;
   if (b >= B || done[b]) return;
-  Optimizer& o = st[b];
-  double gz[kMaxP];
-  double fv;
-  if (status[b] < 0 || !isfinite(lml[b])) {   // not positive definite: a wall, as in the CPU path
-    fv = 1e300;
-    for (int i = 0; i < P; ++i) gz[i] = 0.0;
-  } else {
-    fv = -lml[b];
-    for (int i = 0; i < P; ++i) gz[i] = -grad[b * P + i] * softplus_gradfactor(theta[b * P + i]);
+  Optimizer* so = reinterpret_cast<Optimizer*>(feed_sm) + w;
+  constexpr int NW64 = (int)(sizeof(Optimizer) / 8);
+  unsigned long long* gw = reinterpret_cast<unsigned long long*>(st + b);
+  unsigned long long* sw = reinterpret_cast<unsigned long long*>(so);
+  for (int i = lane; i < NW64; i += 32) sw[i] = gw[i];
+  __syncwarp();
+  if (lane == 0) {
+    Optimizer& o = *so;
+    double gz[kMaxP];
+    double fv;
+    if (status[b] < 0 || !isfinite(lml[b])) {   // not positive definite: a wall, as in the CPU path
+      fv = 1e300;
+      for (int i = 0; i < P; ++i) gz[i] = 0.0;
+    } else {
+      fv = -lml[b];
+      for (int i = 0; i < P; ++i) gz[i] = -grad[b * P + i] * softplus_gradfactor(theta[b * P + i]);
+    }
+    o.feed(fv, gz);
+    if (o.done) {
+      done[b] = 1;
+    } else {
+      for (int i = 0; i < P; ++i) theta[b * P + i] = softplus(o.zt[i]);
+      atomicAdd(n_active, 1);
+    }
   }
-  o.feed(fv, gz);
-  if (o.done) {
-    done[b] = 1;
-  } else {
-    for (int i = 0; i < P; ++i) theta[b * P + i] = softplus(o.zt[i]);
-    atomicAdd(n_active, 1);
-  }
+  __syncwarp();
+  for (int i = lane; i < NW64; i += 32) gw[i] = sw[i];
 }
 
 __global__ void opt_result_kernel(const Optimizer* st, int P, long long B, double* theta_out, double* lml_out, int* iters_out) {
@@ -135,13 +154,19 @@ int cngp_optimize_impl(cngp_ctx* ctx, const cngp_kernel* kernel, const double* t
   const unsigned blocks = (unsigned)((B + 63) / 64);
   opt_init_kernel<<<blocks, 64, 0, s>>>(d_st, d_th0, theta0_stride, P, max_iters, B, d_th, d_map, d_done);
   constexpr int OPT_BLIND = 6;
+  const unsigned feed_blocks = (unsigned)((B + FEED_WPB - 1) / FEED_WPB);
+  const size_t feed_smem = sizeof(Optimizer) * FEED_WPB;
+  if (cudaFuncSetAttribute(opt_feed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feed_smem) != cudaSuccess)
+    return cngp_set_error(ctx, CNGP_ERR_CUDA, "optimize: shared memory attribute");
   int n_active = 1;
   for (int round = 0; n_active > 0 && round * OPT_BLIND <= max_iters + OPT_BLIND; ++round) {
     for (int k = 0; k < OPT_BLIND; ++k) {
       if (cudaMemsetAsync(d_nact, 0, sizeof(int), s) != cudaSuccess) return cngp_set_error(ctx, CNGP_ERR_CUDA, "optimize: memset failed");
       const int rc = cngp_lml_grad_impl(ctx, &kk, d_th, B, d_x, d_y, B, N, d_lml, d_grad, d_st_fit, CNGP_MEM_DEVICE, d_map, d_done);
       if (rc) return rc;
-      opt_feed_kernel<<<blocks, 64, 0, s>>>(d_st, d_lml, d_grad, d_st_fit, P, B, d_th, d_done, d_nact);
+      cngp_ctx_begin(ctx, CNGP_PROF_MISC);
+      opt_feed_kernel<<<feed_blocks, FEED_WPB * 32, feed_smem, s>>>(d_st, d_lml, d_grad, d_st_fit, P, B, d_th, d_done, d_nact);
+      cngp_ctx_end(ctx);
     }
     if (cudaMemcpyAsync(&n_active, d_nact, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
         cudaStreamSynchronize(s) != cudaSuccess)
