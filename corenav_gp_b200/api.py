@@ -235,8 +235,10 @@ class GpContext:
         t = np.ascontiguousarray(time_array, dtype=np.float64)
         s = np.ascontiguousarray(slip_array, dtype=np.float64)
         B, n = t.shape
-        span = float(t.max() - t.min())
-        m_cap = int(np.ceil(span)) + horizon + 2
+        # gp_slip_node.py:45,59-61: len(arange(min, max + horizon, 1)) - n published points; the same for every window
+        # of a batch (the library checks), so the outputs can be allocated at their exact size
+        lens = np.ceil((t.max(axis=1) + float(horizon)) - t.min(axis=1))
+        m_cap = max(1, int(lens.max()) - n)
         mean = np.empty((B, m_cap))
         sigma = np.empty((B, m_cap))
         m_out = C.c_int32(0)
@@ -253,6 +255,8 @@ class GpContext:
                                          status.ctypes.data)
         self._check(rc, "cngp_gp_slip_batch")
         m = m_out.value
+        if m == m_cap:
+            return mean, sigma, status
         return mean[:, :m].copy(), sigma[:, :m].copy(), status
 
     # ------------------------------------------------------------------------------------------------------

@@ -198,6 +198,14 @@ extern "C" int cngp_optimize_batch_mem(cngp_ctx* ctx, const cngp_kernel* kernel,
   return cngp_optimize_impl(ctx, kernel, theta0, theta0_stride, x, y, B, N, max_iters, theta_out, lml_out, iters_out, mem);
 }
 
+namespace {
+// gp_slip_node.py:45,59-61: X_ = arange(X.min(), X.max() + horizon, 1); the published part is X_[len(X):]
+__global__ void grid_fill_kernel(const double* t0, int n, long long M, long long B, double* grid) {
+  for (long long b = blockIdx.x; b < B; b += gridDim.x)
+    for (long long k = threadIdx.x; k < M; k += blockDim.x) grid[b * M + k] = t0[b] + (double)(n + k);
+}
+}  // namespace
+
 extern "C" int cngp_gp_slip_batch(cngp_ctx* ctx, const cngp_kernel* kernel, const double* theta, int64_t theta_stride,
                                   const double* time_array, const double* slip_array, int64_t B, int32_t n,
                                   int32_t horizon, int32_t m_cap, double* mean, double* sigma, int32_t* m_out,
@@ -232,30 +240,47 @@ extern "C" int cngp_gp_slip_batch(cngp_ctx* ctx, const cngp_kernel* kernel, cons
   if (M <= 0) return CNGP_OK;
   if (M > m_cap) return cngp_set_error(ctx, CNGP_ERR_INVALID, "gp_slip: m_cap too small");
 
-  std::vector<double> xtr((size_t)B * ntr), ytr((size_t)B * ntr), grid((size_t)B * M);
-  for (int64_t b = 0; b < B; ++b) {
-    memcpy(&xtr[(size_t)b * ntr], time_array + b * n, sizeof(double) * ntr);
-    memcpy(&ytr[(size_t)b * ntr], slip_array + b * n, sizeof(double) * ntr);
-    for (int64_t k = 0; k < M; ++k) grid[(size_t)b * M + k] = t0[b] + (double)(n + k);
-  }
-  std::vector<double> fitted;
-  const double* th = theta;
+  // Everything between the caller's arrays and the kernels stays on the device: the training split is a strided upload
+  // (no host repacking), the prediction grid is generated in place, the fitted hyper-parameters never leave the GPU, and
+  // the outputs come back with one strided copy each.  (Round 1 staged x, y, the B x M grid, mean and sigma through
+  // pageable std::vectors and uploaded x, y twice - at B = 4096 half of the call.)
+  cudaStream_t s = cngp_ctx_stream(ctx);
+  enum { SLOT_CB_XTR = 44, SLOT_CB_YTR, SLOT_CB_GRID, SLOT_CB_MU, SLOT_CB_SG, SLOT_CB_TH, SLOT_CB_T0, SLOT_CB_STATUS };
+  double* d_xtr = (double*)cngp_ctx_buf(ctx, SLOT_CB_XTR, sizeof(double) * (size_t)B * ntr);
+  double* d_ytr = (double*)cngp_ctx_buf(ctx, SLOT_CB_YTR, sizeof(double) * (size_t)B * ntr);
+  double* d_grid = (double*)cngp_ctx_buf(ctx, SLOT_CB_GRID, sizeof(double) * (size_t)B * M);
+  double* d_mu = (double*)cngp_ctx_buf(ctx, SLOT_CB_MU, sizeof(double) * (size_t)B * M);
+  double* d_sg = (double*)cngp_ctx_buf(ctx, SLOT_CB_SG, sizeof(double) * (size_t)B * M);
+  const size_t th_doubles = theta ? (theta_stride ? (size_t)B * theta_stride : (size_t)P) : (size_t)B * P;
+  double* d_th = (double*)cngp_ctx_buf(ctx, SLOT_CB_TH, sizeof(double) * th_doubles);
+  double* d_t0 = (double*)cngp_ctx_buf(ctx, SLOT_CB_T0, sizeof(double) * (size_t)B);
+  int* d_status = (int*)cngp_ctx_buf(ctx, SLOT_CB_STATUS, sizeof(int) * (size_t)B);
+  if (!d_xtr || !d_ytr || !d_grid || !d_mu || !d_sg || !d_th || !d_t0 || !d_status)
+    return cngp_set_error(ctx, CNGP_ERR_NOMEM, "gp_slip: device allocation failed");
+  if (cudaMemcpy2DAsync(d_xtr, sizeof(double) * ntr, time_array, sizeof(double) * n, sizeof(double) * ntr, (size_t)B,
+                        cudaMemcpyHostToDevice, s) != cudaSuccess ||
+      cudaMemcpy2DAsync(d_ytr, sizeof(double) * ntr, slip_array, sizeof(double) * n, sizeof(double) * ntr, (size_t)B,
+                        cudaMemcpyHostToDevice, s) != cudaSuccess ||
+      cudaMemcpyAsync(d_t0, t0.data(), sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+      (theta && cudaMemcpyAsync(d_th, theta, sizeof(double) * th_doubles, cudaMemcpyHostToDevice, s) != cudaSuccess))
+    return cngp_set_error(ctx, CNGP_ERR_CUDA, "gp_slip: upload failed");
+  grid_fill_kernel<<<(unsigned)std::min<int64_t>(B, 65535), 128, 0, s>>>(d_t0, n, M, B, d_grid);
   int64_t th_stride = theta_stride;
   if (!theta) {                                   // gp_slip_node.py:35-36: all-ones start, then m.optimize()
-    fitted.resize((size_t)B * P);
-    const int rc = cngp_optimize_batch(ctx, &kk, nullptr, 0, xtr.data(), ytr.data(), B, ntr, 1000, fitted.data(), nullptr, nullptr);
+    const int rc = cngp_optimize_impl(ctx, &kk, nullptr, 0, d_xtr, d_ytr, B, ntr, 1000, d_th, nullptr, nullptr, CNGP_MEM_DEVICE);
     if (rc) return rc;
-    th = fitted.data();
     th_stride = P;
   }
-  std::vector<double> mu((size_t)B * M), sg((size_t)B * M);
-  const int rc = cngp_predict_impl(ctx, &kk, th, th_stride, xtr.data(), ytr.data(), grid.data(), M, B, ntr, (int32_t)M,
-                                   mu.data(), sg.data(), nullptr, status, CNGP_MEM_HOST, /*sigma_mode=*/1);
+  const int rc = cngp_predict_impl(ctx, &kk, d_th, th_stride, d_xtr, d_ytr, d_grid, M, B, ntr, (int32_t)M, d_mu, d_sg, nullptr,
+                                   d_status, CNGP_MEM_DEVICE, /*sigma_mode=*/1);
   if (rc) return rc;
-  for (int64_t b = 0; b < B; ++b) {
-    memcpy(mean + b * m_cap, &mu[(size_t)b * M], sizeof(double) * M);
-    memcpy(sigma + b * m_cap, &sg[(size_t)b * M], sizeof(double) * M);
-  }
+  if (cudaMemcpy2DAsync(mean, sizeof(double) * m_cap, d_mu, sizeof(double) * M, sizeof(double) * M, (size_t)B,
+                        cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      cudaMemcpy2DAsync(sigma, sizeof(double) * m_cap, d_sg, sizeof(double) * M, sizeof(double) * M, (size_t)B,
+                        cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      (status && cudaMemcpyAsync(status, d_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s) != cudaSuccess) ||
+      cudaStreamSynchronize(s) != cudaSuccess)
+    return cngp_set_error(ctx, CNGP_ERR_CUDA, "gp_slip: download failed");
   *m_out = (int32_t)M;
   return CNGP_OK;
 }
