@@ -480,6 +480,7 @@ static void launch_fit_w(const FitArgs& fa, long long nprob, cudaStream_t s) {
   // row tiles (nt) must fit NW workers x T slots
   if (fa.nt <= 8) launch_fit_k<KID, 4, 2>(fa, nprob, s);
   else if (fa.nt <= 16) launch_fit_k<KID, 8, 2>(fa, nprob, s);
+  else if (fa.nt <= 18) launch_fit_k<KID, 9, 2>(fa, nprob, s);   // the reference's own window (134 of 149 samples): two CTAs per SM
   else launch_fit_k<KID, FIT_NW_FULL, FIT_T_FULL>(fa, nprob, s);
 }
 static void launch_fit(int kid, const FitArgs& fa, long long nprob, cudaStream_t s) {

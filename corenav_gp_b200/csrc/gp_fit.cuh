@@ -155,7 +155,7 @@ __device__ __forceinline__ int fit_residue(int w) {
 
 // NW workers, T row-tile slots per worker: nt <= NW * T.
 template <int KID, int NW, int T>
-__global__ void __launch_bounds__((NW + 1) * 32, NW * T > 16 ? 1 : 2) gp_fit_kernel(const FitArgs a) {
+__global__ void __launch_bounds__((NW + 1) * 32, NW * T > 18 ? 1 : 2) gp_fit_kernel(const FitArgs a) {
   constexpr int FIT_THREADS = (NW + 1) * 32;
   extern __shared__ __align__(128) double pool[];               // tile pool, see fit_pool_tiles
   __shared__ __align__(16) double fx[NPAD], fxx[NPAD], fc[NPAD], fs[NPAD];   // per-point features
